@@ -1,0 +1,184 @@
+/*
+ * umbrella_b200 -- C ABI of the B200-native speculative-decoding verify path.
+ *
+ * Drop-in boundary for the hot path of Infini-AI-Lab/UMbreLLa (reference @ ff1ac17).  Every entry
+ * point takes plain device pointers, sizes and a cudaStream_t (as void*); no torch types, no
+ * allocation, no host synchronisation, no default-stream use inside.  Return value: 0 = ok,
+ * negative = argument / capability error (see UMB_ERR_*), positive = cudaError_t.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   (i)   awq_ext.gemm_forward_cuda / awq_ext.dequantize_weights_cuda, called from
+ *         umbrella/quantization/awq_utils.py:70-77            -> umb_awq_repack, umb_awq_gemm_f16,
+ *                                                                umb_awq_dequantize_f16
+ *         torch F.linear for fp16 weights (lm_head llama.py:321, fp16 models llama.py:87-110)
+ *                                                             -> umb_gemm_f16
+ *   (ii)  flashinfer.single_prefill_with_kv_cache(custom_mask=...), called from
+ *         umbrella/attn/cache.py:77-85; KV append cache.py:53-65 -> umb_tree_attn_f16, umb_rope_append_f16
+ *   (iii) the accept block of verify() static_speculation_engine.py:312-349 /
+ *         dynamic_speculation_engine.py:283-323 and KV_Cache.gather_kv_incremental
+ *         cache.py:41-49,136-144                               -> umb_tree_accept, umb_kv_gather
+ *   glue  flashinfer.rmsnorm (model_utils.py:62), apply_rotary_pos_emb (model_utils.py:24-52),
+ *         silu*up / residual adds (llama.py:293-301), F.embedding (llama.py:312), argmax
+ *         (static_speculation_engine.py:307)                   -> umb_rmsnorm_f16, umb_silu_mul_f16,
+ *                                                                umb_add_f16, umb_embedding_f16, umb_argmax_f32
+ */
+#ifndef UMBRELLA_B200_H
+#define UMBRELLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* umb_stream_t; /* cudaStream_t */
+
+#define UMB_OK 0
+#define UMB_ERR_ARG (-1)         /* bad pointer / size / alignment */
+#define UMB_ERR_UNSUPPORTED (-2) /* shape or option outside what the kernels implement */
+#define UMB_ERR_WORKSPACE (-3)   /* workspace too small */
+#define UMB_ERR_DRIVER (-4)      /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+
+const char* umb_version(void);
+const char* umb_error_string(int code);
+/* Number of kernel launches issued through this library since load (all entry points). */
+unsigned long long umb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (i) AWQ INT4 GEMM  --  y[M,N] = x[M,K] . W,  W[k, n] = (q[k,n] - z[k/g,n]) * s[k/g,n]
+ *
+ * Weights are repacked ONCE (at AwqLinear.init_parameters / copy time) from the AutoAWQ "GEMM"
+ * checkpoint layout into a K-major tile stream laid out for TMA bulk copies:
+ *   tile t (128 output features) x group g (128 input features) -> one 8512-byte record
+ *   [2 k-blocks][2 chunks][128 rows][16 B nibbles] | [128] fp16 scales | [128] 4-bit zeros
+ * Same 0.5 + 2/128 + 0.5/128 bytes per parameter as the checkpoint.  Several checkpoint matrices
+ * that share K can be packed into one stream (q|k|v, gate|up) through the row mapping
+ *   packed_row(n) = (n / row_block) * row_stride + row_offset + n % row_block .
+ * ---------------------------------------------------------------------------------------------- */
+size_t umb_awq_packed_bytes(int K, int N_total, int group);
+
+/* qweight int32 [K, N/8], qzeros int32 [K/group, N/8], scales fp16 [K/group, N]  (device, AutoAWQ
+ * nibble order [0,4,1,5,2,6,3,7]) -> rows of `packed` (device, umb_awq_packed_bytes(K, N_total)).
+ * The caller zero-fills `packed` once before the first repack into it. */
+int umb_awq_repack(const int32_t* qweight, const int32_t* qzeros, const void* scales, int K, int N, int group,
+                   void* packed, int N_total, int row_block, int row_stride, int row_offset, umb_stream_t stream);
+
+/* awq_ext.dequantize_weights_cuda drop-in: fp16 [K, N] = fp16((q - z) * s). */
+int umb_awq_dequantize_f16(const int32_t* qweight, const int32_t* qzeros, const void* scales, int K, int N,
+                           int group, void* out, umb_stream_t stream);
+
+/* Inverse of the repack for tests: packed stream -> fp16 [N_total, K] (row = packed row). */
+int umb_awq_unpack_f16(const void* packed, int K, int N_total, int group, void* out, umb_stream_t stream);
+
+/* Epilogue applied by the CTA that completes an output tile. */
+enum {
+    UMB_EPI_STORE = 0,    /* y[m, n] = fp16(acc) (+ bias[n])                                   */
+    UMB_EPI_RESIDUAL = 1, /* y[m, n] = fp16(acc) +_fp16 residual[m, n]   (llama.py:293,301)      */
+    UMB_EPI_SILU_MUL = 2, /* packed rows interleave 64 gate | 64 up per tile;
+                             y[m, 64 t + r] = fp16(silu(fp16(gate))) *_fp16 fp16(up)  (llama.py:296-299) */
+    UMB_EPI_LOGITS = 3    /* y is fp32 [M, N]: float(fp16(acc)); optional running arg-max keys   */
+};
+typedef struct {
+    int mode;
+    const void* bias;            /* fp16 [N] or NULL                                              */
+    const void* residual;        /* fp16 [M, ld_residual] (mode 1); may alias y                   */
+    int64_t ld_residual;
+    unsigned long long* argmax;  /* mode 3: [M] keys, (orderable(fp16 logit) << 32) | ~index; caller
+                                    zero-fills; NULL = no arg-max                                  */
+} umb_epilogue_t;
+
+size_t umb_gemm_workspace_bytes(int M, int K, int N_total);
+
+/* x fp16 [M, K] row-major (leading dimension ldx elements), y fp16 [M, N_out] (ldy elements),
+ * 1 <= M <= 128 per call.  `workspace` must be zero-filled once after allocation; the kernel
+ * leaves it clean.  N_total % 8 == 0, K % 128 == 0, group == 128. */
+int umb_awq_gemm_f16(const void* x, int64_t ldx, const void* packed, void* y, int64_t ldy, int M, int K,
+                     int N_total, int group, const umb_epilogue_t* epilogue, void* workspace, size_t workspace_bytes,
+                     umb_stream_t stream);
+
+/* fp16 weights W [N, K] row-major (torch Linear layout): y[M,N] = x . W^T.  Same contract. */
+int umb_gemm_f16(const void* x, int64_t ldx, const void* w, int64_t ldw, void* y, int64_t ldy, int M, int K, int N,
+                 const umb_epilogue_t* epilogue, void* workspace, size_t workspace_bytes, umb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (ii) tree-masked GQA attention over the KV cache
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+    UMB_MASK_TREE = 0,   /* row i sees [0, prefix_len) and prefix_len + j for every set bit j of
+                            tree_bits[i, :] (u32 words, bit j%32 of word j/32)                    */
+    UMB_MASK_DENSE = 1,  /* row i sees j iff dense_mask[i * mask_stride + j] != 0  (bool / u8)     */
+    UMB_MASK_CAUSAL = 2  /* row i sees j <= prefix_len + i   (prefill / append)                    */
+};
+typedef struct {
+    int mask_mode;
+    int prefix_len;                /* committed prefix n (modes 0, 2)                              */
+    const int32_t* dyn;            /* optional device int32[2] = {prefix_len, kv_len}; overrides the
+                                      host values (CUDA-graph replay with a moving prefix)          */
+    const uint32_t* tree_bits;     /* [qo, tree_words]                                             */
+    int tree_words;
+    const uint8_t* dense_mask;
+    int64_t mask_stride;
+} umb_attn_mask_t;
+
+size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int head_dim, int max_kv_len);
+
+/* q fp16 [qo, Hq, D]; k/v: base of this layer's cache, token stride / head stride in elements
+ * ([S,Hkv,D]: tok = Hkv*D, head = D;  [Hkv,S,D]: tok = D, head = S*D); out fp16 [qo, Hq, D].
+ * kv_len = number of valid cache rows (after the append).  sm_scale <= 0 -> 1/sqrt(D). */
+int umb_tree_attn_f16(const void* q, const void* k_cache, const void* v_cache, void* out, int qo, int kv_len,
+                      int num_q_heads, int num_kv_heads, int head_dim, int64_t kv_tok_stride, int64_t kv_head_stride,
+                      const umb_attn_mask_t* mask, float sm_scale, float soft_cap, void* workspace,
+                      size_t workspace_bytes, umb_stream_t stream);
+
+/* RoPE (HF half-split, fp16 arithmetic, fp16 tables [S, D]) on q and k, then append k (rotated) and
+ * v at cache rows [kv_offset, kv_offset + qo).  qkv fp16 [qo, (Hq + 2 Hkv) * D] (q | k | v);
+ * q_out fp16 [qo, Hq, D].  kv_offset_dev (optional device int32) overrides kv_offset. */
+int umb_rope_append_f16(const void* qkv, int64_t ld_qkv, void* q_out, void* k_cache, void* v_cache, const void* cos,
+                        const void* sin, const int64_t* position_ids, int qo, int num_q_heads, int num_kv_heads,
+                        int head_dim, int64_t kv_tok_stride, int64_t kv_head_stride, int kv_offset,
+                        const int32_t* kv_offset_dev, umb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (iii) tree accept + KV gather (integer, bit-exact with the reference)
+ * ---------------------------------------------------------------------------------------------- */
+/* In:  sampled int64[N] (target token after each node), tokens int64[S], position_ids int64[S],
+ *      parents int32[N] (parents[0] = 0, parent < child), depth int32[N], num_nodes (or
+ *      state[0] if state != NULL), eos int64[n_eos].
+ * Out: tokens[n : n+len+1], position_ids updated exactly as the reference's verify() does;
+ *      result int32[4 + N]: {accept_len, continue, new_num_nodes, bonus_lo32, path_abs[0..len)}
+ *      (device or mapped-pinned memory); state[0] = new_num_nodes, state[1] = new_num_nodes + N
+ *      if state != NULL. */
+int umb_tree_accept(const int64_t* sampled, int64_t* tokens, int64_t* position_ids, const int32_t* parents,
+                    const int32_t* depth, int N, int num_nodes, int32_t* state, const int64_t* eos, int n_eos,
+                    int32_t* result, umb_stream_t stream);
+
+/* cache[plane, offset + j, :] = cache[plane, path[j], :] for j < len, for every plane
+ * (plane = layer for [L,S,Hkv,D]; layer*head for [L,Hkv,S,D]); K and V in one launch.
+ * path/len are read from `result` as written by umb_tree_accept (device memory).  Rows
+ * [offset + len, zero_upto) are zero-filled when zero_upto > 0 (the reference zero-fills the
+ * whole tail, cache.py:46-47). */
+int umb_kv_gather(void* k_cache, void* v_cache, int num_planes, int64_t plane_stride_bytes, int64_t row_stride_bytes,
+                  int row_bytes, const int32_t* result, int offset, const int32_t* offset_dev, int zero_upto,
+                  umb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * glue
+ * ---------------------------------------------------------------------------------------------- */
+int umb_rmsnorm_f16(const void* x, const void* weight, void* y, int rows, int hidden, float eps, umb_stream_t stream);
+int umb_silu_mul_f16(const void* gate, const void* up, void* y, int64_t n, umb_stream_t stream);
+int umb_add_f16(const void* a, const void* b, void* y, int64_t n, umb_stream_t stream);
+int umb_embedding_f16(const int64_t* ids, const void* table, void* y, int rows, int hidden, umb_stream_t stream);
+/* first-occurrence arg-max over each row of fp32 logits [rows, vocab] -> int64[rows] */
+int umb_argmax_f32(const float* logits, int64_t ld, int rows, int vocab, int64_t* out, umb_stream_t stream);
+/* decode the UMB_EPI_LOGITS arg-max keys into int64 token ids */
+int umb_argmax_keys_to_ids(const unsigned long long* keys, int rows, int64_t* out, umb_stream_t stream);
+
+/* Debug probes (tests only): one 128x16x64 UMMA with A from tensor memory / shared memory. */
+int umb_probe_umma(const void* a /*fp16 [128,64]*/, const void* b /*fp16 [16,64]*/, float* d /*[128,16]*/, int mode,
+                   umb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMBRELLA_B200_H */
