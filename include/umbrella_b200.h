@@ -178,6 +178,67 @@ int umb_argmax_keys_to_ids(const unsigned long long* keys, int rows, int64_t* ou
 int umb_probe_umma(const void* a /*fp16 [128,64]*/, const void* b /*fp16 [16,64]*/, float* d /*[128,16]*/, int mode,
                    umb_stream_t stream);
 
+
+/* Cross-check of the packed AWQ stream on CUDA cores (tests only; not a product path). */
+int umb_awq_gemm_f16_simt(const void* x, int64_t ldx, const void* packed, void* y, int64_t ldy, int M, int K, int N_total,
+                          umb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * native forward driver: one call enqueues the whole Llama forward of LlamaAwq.inference /
+ * Llama.inference (reference umbrella/models/llama.py:305-322, 117-134; layer_compute :262-303,
+ * :75-114) on `stream` -- embedding, L x {RMSNorm, fused q|k|v GEMM, RoPE + KV append, tree
+ * attention, o-proj GEMM (+residual), RMSNorm, fused gate|up GEMM (SiLU*up epilogue), down GEMM
+ * (+residual)}, final RMSNorm, lm_head GEMM (fp32 logits, optional arg-max keys).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* input_norm;  /* fp16 [H]                                                             */
+    const void* post_norm;   /* fp16 [H]                                                             */
+    const void* wqkv;        /* awq: packed stream, rows q|k|v; fp16: [(Hq+2Hkv)*D, H] row-major      */
+    const void* wo;          /* awq: packed stream [H rows, K = Hq*D]; fp16: [H, Hq*D]                */
+    const void* wgu;         /* rows interleaved 64 gate | 64 up per 128-row tile, 2*I rows total     */
+    const void* wdown;       /* [H rows, K = I]                                                       */
+} umb_llama_layer_t;
+
+typedef struct {
+    int hidden_size, intermediate_size, num_layers, num_q_heads, num_kv_heads, head_dim, vocab;
+    float rms_eps;
+    int awq;                 /* 1 = layer weights are AWQ packed streams, 0 = fp16 matrices           */
+    int max_length;          /* S: rows of the KV cache and of the cos/sin tables                     */
+    const umb_llama_layer_t* layers; /* host array [num_layers]                                       */
+    const void* embed;       /* fp16 [V, H]                                                           */
+    const void* final_norm;  /* fp16 [H]                                                              */
+    const void* lm_head;     /* fp16 [V, H] (never quantised, llama.py:321)                           */
+    const void* cos;         /* fp16 [S, D]                                                           */
+    const void* sin;         /* fp16 [S, D]                                                           */
+    void* k_cache;           /* fp16 [L, S, Hkv, D]  (KV_Cache layout, cache.py:18-34)                */
+    void* v_cache;
+    /* activations for up to 128 rows: hidden [128,H], normed [128,H], qkv [128,(Hq+2Hkv)*D],
+     * q_rot [128,Hq*D], attn_out [128,Hq*D], act [128,I]                                             */
+    void* hidden;
+    void* normed;
+    void* qkv;
+    void* q_rot;
+    void* attn_out;
+    void* act;
+    void* gemm_ws;           /* zero-filled once by the caller; >= umb_llama_gemm_ws_bytes()          */
+    size_t gemm_ws_bytes;
+    void* attn_ws;
+    size_t attn_ws_bytes;
+} umb_llama_t;
+
+size_t umb_llama_gemm_ws_bytes(int hidden, int intermediate, int num_q_heads, int num_kv_heads, int head_dim,
+                               int vocab);
+
+/* rows tokens appended at cache rows [kv_offset, kv_offset + rows) (KV_Cache.update_kv_cache appends,
+ * cache.py:53-65).  rows > 128 are processed in chunks of 128 (chunked prefill); `mask` describes
+ * the rows of the whole call (dense: row r of the call = mask row r; causal/tree: prefix_len is the
+ * number of cache rows visible to every row of the call, normally kv_offset).
+ * logits: fp32 [rows - logits_from_row, vocab] for call rows >= logits_from_row, or NULL.
+ * argmax_keys: optional [rows - logits_from_row] u64 keys (zero-filled by the caller). */
+int umb_llama_forward(const umb_llama_t* model, const int64_t* input_ids, const int64_t* position_ids, int rows,
+                      int kv_offset, const umb_attn_mask_t* mask, float* logits, int logits_from_row,
+                      unsigned long long* argmax_keys, umb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

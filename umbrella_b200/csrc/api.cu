@@ -1,0 +1,39 @@
+// Library bookkeeping: version, error strings, launch counter, device properties.
+#include <atomic>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace umb {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+}  // namespace umb
+
+extern "C" const char* umb_version(void) { return "umbrella_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* umb_error_string(int code) {
+    switch (code) {
+        case UMB_OK: return "ok";
+        case UMB_ERR_ARG: return "invalid argument (pointer, size or alignment)";
+        case UMB_ERR_UNSUPPORTED: return "shape or option not supported by the sm_100a kernels";
+        case UMB_ERR_WORKSPACE: return "workspace too small";
+        case UMB_ERR_DRIVER: return "CUDA driver entry point unavailable (cuTensorMapEncodeTiled)";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+extern "C" unsigned long long umb_launch_count(void) { return umb::g_launches.load(std::memory_order_relaxed); }

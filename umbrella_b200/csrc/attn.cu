@@ -1,0 +1,421 @@
+// (ii) tree-masked grouped-query attention over the KV cache.
+//
+// Replaces flashinfer.single_prefill_with_kv_cache(custom_mask=...) as called from
+// KV_Cache.compute_attention (reference umbrella/attn/cache.py:67-87) and the torch path of
+// StaticKV_Cache.compute_attention (cache.py:169-192).
+//
+// Shape of the problem at verify time: qo = tree size (13..505) query tokens, Hq/Hkv = 8 (or 4)
+// query heads share each KV head, kv = prefix + tree rows.  Every KV row is therefore used by
+// G * qo query rows: the kernel flattens (token, head-in-group) into one row index per KV head so
+// that a 64-row CTA tile re-uses each K/V row 64 times from shared memory, streams K/V exactly once
+// per (row tile, split) with 16-byte cp.async loads (coalesced, L1-bypassing), runs QK^T and PV on
+// mma.sync m16n8k16 (fp16 in, fp32 accumulate) and keeps the softmax in fp32 with quad shuffles.
+// The mask is never materialised for the tree case: rows see [0, prefix_len) unconditionally and
+// prefix_len + j iff bit j of their ancestor bitmask is set.  Long contexts are split along KV
+// (grid.z) and merged by a second kernel with a log-sum-exp reduction.
+#include "common.cuh"
+#include "internal.h"
+
+namespace umb {
+
+struct AttnParams {
+    const __half* q;
+    const __half* k;
+    const __half* v;
+    __half* out;
+    int qo, kv_len, Hq, Hkv, G;
+    int64_t kv_tok_stride, kv_head_stride;
+    int mask_mode, prefix_len;
+    const int32_t* dyn;
+    const uint32_t* tree_bits;
+    int tree_words;
+    const uint8_t* dense_mask;
+    int64_t mask_stride;
+    float scale_log2;   // sm_scale * log2(e)
+    float soft_cap;     // 0 = off
+    float sm_scale;
+    int splits;
+    float* part_o;      // [splits][Hkv * qo * G][D]
+    float2* part_ml;    // [splits][Hkv * qo * G]  (running max in the log2 domain, running sum)
+};
+
+constexpr int kAttnThreads = 128;
+constexpr int kBM = 64;   // query rows per CTA (16 per warp)
+constexpr int kBN = 64;   // kv rows per tile
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// smem tile: kBN rows x D halves, 16-byte chunks XOR-swizzled by (row & 7)
+template <int D>
+__device__ __forceinline__ __half* tile_ptr(__half* base, int row, int chunk) {
+    return base + row * D + ((chunk ^ (row & 7)) << 3);
+}
+
+template <int D>
+__device__ __forceinline__ void load_tile(__half* smem, const __half* gbase, int64_t tok_stride, int row0, int kv_hi) {
+    constexpr int kChunks = D / 8;
+    for (int i = threadIdx.x; i < kBN * kChunks; i += kAttnThreads) {
+        const int r = i / kChunks, c = i % kChunks;
+        const int row = row0 + r;
+        const bool ok = row < kv_hi;
+        cp_async16(tile_ptr<D>(smem, r, c), gbase + (int64_t)(ok ? row : 0) * tok_stride + c * 8, ok);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [2][kBN][D]
+    __half* sV = sK + 2 * kBN * D;                                     // [2][kBN][D]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    const int hkv = blockIdx.y, split = blockIdx.z;
+    const int rows_total = p.qo * p.G;
+    const int prefix_len = p.dyn ? p.dyn[0] : p.prefix_len;
+    const int kv_len = p.dyn ? p.dyn[1] : p.kv_len;
+
+    const int row_base = blockIdx.x * kBM + warp * 16;
+    // the two rows this thread owns inside its warp's 16-row slab
+    int row[2], tok[2];
+    bool row_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        row[i] = row_base + g4 + 8 * i;
+        row_ok[i] = row[i] < rows_total;
+        tok[i] = row_ok[i] ? row[i] / p.G : 0;
+    }
+
+    // ---- Q fragments (A operand), straight from global ----
+    uint32_t qf[D / 16][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int hq = hkv * p.G + (row_ok[i] ? row[i] % p.G : 0);
+        const __half* qr = p.q + ((int64_t)tok[i] * p.Hq + hq) * D;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+            uint32_t lo = 0, hi = 0;
+            if (row_ok[i]) {
+                lo = *reinterpret_cast<const uint32_t*>(qr + ks * 16 + t4 * 2);
+                hi = *reinterpret_cast<const uint32_t*>(qr + ks * 16 + 8 + t4 * 2);
+            }
+            qf[ks][i] = lo;
+            qf[ks][2 + i] = hi;
+        }
+    }
+
+    // ---- kv range of this CTA ----
+    int kv_hi = kv_len;
+    if (p.mask_mode == UMB_MASK_CAUSAL) {
+        const int last_row = min(rows_total, (int)(blockIdx.x + 1) * kBM) - 1;
+        kv_hi = min(kv_hi, prefix_len + last_row / p.G + 1);
+    } else if (p.mask_mode == UMB_MASK_TREE) {
+        kv_hi = min(kv_hi, prefix_len + p.qo);
+    }
+    const int n_tiles = (kv_hi + kBN - 1) / kBN;
+    const int tiles_per_split = (n_tiles + p.splits - 1) / p.splits;
+    const int tile_lo = split * tiles_per_split;
+    const int tile_hi = min(n_tiles, tile_lo + tiles_per_split);
+
+    const __half* kg = p.k + (int64_t)hkv * p.kv_head_stride;
+    const __half* vg = p.v + (int64_t)hkv * p.kv_head_stride;
+
+    float o_acc[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+    if (tile_lo < tile_hi) {
+        load_tile<D>(sK, kg, p.kv_tok_stride, tile_lo * kBN, kv_hi);
+        load_tile<D>(sV, vg, p.kv_tok_stride, tile_lo * kBN, kv_hi);
+        cp_async_commit();
+    }
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        const int buf = (tile - tile_lo) & 1;
+        if (tile + 1 < tile_hi) {
+            load_tile<D>(sK + (buf ^ 1) * kBN * D, kg, p.kv_tok_stride, (tile + 1) * kBN, kv_hi);
+            load_tile<D>(sV + (buf ^ 1) * kBN * D, vg, p.kv_tok_stride, (tile + 1) * kBN, kv_hi);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const __half* tK = sK + buf * kBN * D;
+        const __half* tV = sV + buf * kBN * D;
+
+        // ---- S = Q K^T  (16 x 64 per warp) ----
+        float s[kBN / 8][4];
+#pragma unroll
+        for (int i = 0; i < kBN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+#pragma unroll
+            for (int nb = 0; nb < kBN / 8; nb += 2) {
+                uint32_t b[4];
+                const int r = nb * 8 + (lane & 7) + ((lane >> 4) << 3);
+                const int c = ks * 2 + ((lane >> 3) & 1);
+                ldmatrix_x4(b, tile_ptr<D>(const_cast<__half*>(tK), r, c));
+                mma_16816(s[nb], qf[ks], b[0], b[1]);
+                mma_16816(s[nb + 1], qf[ks], b[2], b[3]);
+            }
+        }
+
+        // ---- scale, soft-cap, mask ----
+        const int col0 = tile * kBN;
+        const bool need_mask = (col0 + kBN > kv_hi) || (p.mask_mode == UMB_MASK_DENSE) || (col0 + kBN > prefix_len);
+#pragma unroll
+        for (int nb = 0; nb < kBN / 8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float x = s[nb][e];
+                if (p.soft_cap > 0.f) {
+                    x = p.soft_cap * tanhf(x * p.sm_scale / p.soft_cap) * 1.4426950408889634f;
+                } else {
+                    x *= p.scale_log2;
+                }
+                if (need_mask) {
+                    const int ri = e >> 1;
+                    const int j = col0 + nb * 8 + t4 * 2 + (e & 1);
+                    bool ok = row_ok[ri] && j < kv_hi;
+                    if (ok) {
+                        if (p.mask_mode == UMB_MASK_TREE) {
+                            if (j >= prefix_len) {
+                                const int b = j - prefix_len;
+                                ok = (p.tree_bits[(int64_t)tok[ri] * p.tree_words + (b >> 5)] >> (b & 31)) & 1u;
+                            }
+                        } else if (p.mask_mode == UMB_MASK_CAUSAL) {
+                            ok = j <= prefix_len + tok[ri];
+                        } else {
+                            ok = p.dense_mask[(int64_t)tok[ri] * p.mask_stride + j] != 0;
+                        }
+                    }
+                    if (!ok) x = -INFINITY;
+                }
+                s[nb][e] = x;
+            }
+        }
+
+        // ---- online softmax (rows g4 and g4 + 8) ----
+        float m_new[2], corr[2];
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nb = 0; nb < kBN / 8; ++nb) mx = fmaxf(mx, fmaxf(s[nb][2 * ri], s[nb][2 * ri + 1]));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            m_new[ri] = fmaxf(m_run[ri], mx);
+            const float m_use = m_new[ri] == -INFINITY ? 0.f : m_new[ri];
+            corr[ri] = exp2f(m_run[ri] - m_use);                    // m_run = -inf -> 0
+            float sum = 0.f;
+#pragma unroll
+            for (int nb = 0; nb < kBN / 8; ++nb) {
+                const float p0 = exp2f(s[nb][2 * ri] - m_use), p1 = exp2f(s[nb][2 * ri + 1] - m_use);
+                s[nb][2 * ri] = p0;
+                s[nb][2 * ri + 1] = p1;
+                sum += p0 + p1;
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            l_run[ri] = l_run[ri] * corr[ri] + sum;
+            m_run[ri] = m_new[ri];
+        }
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+            o_acc[i][0] *= corr[0];
+            o_acc[i][1] *= corr[0];
+            o_acc[i][2] *= corr[1];
+            o_acc[i][3] *= corr[1];
+        }
+
+        // ---- O += P V ----
+#pragma unroll
+        for (int ks = 0; ks < kBN / 16; ++ks) {
+            uint32_t a[4];
+            a[0] = pack_half2(s[2 * ks][0], s[2 * ks][1]);
+            a[1] = pack_half2(s[2 * ks][2], s[2 * ks][3]);
+            a[2] = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+            a[3] = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+            for (int db = 0; db < D / 8; db += 2) {
+                uint32_t b[4];
+                const int r = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                const int c = db + (lane >> 4);
+                ldmatrix_x4_trans(b, tile_ptr<D>(const_cast<__half*>(tV), r, c));
+                mma_16816(o_acc[db], a, b[0], b[1]);
+                mma_16816(o_acc[db + 1], a, b[2], b[3]);
+            }
+        }
+        __syncthreads();   // the buffer is re-filled two iterations later
+    }
+
+    // ---- write-out ----
+    if (p.splits == 1) {
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri) {
+            if (!row_ok[ri]) continue;
+            const float inv = l_run[ri] > 0.f ? 1.f / l_run[ri] : 0.f;
+            const int hq = hkv * p.G + row[ri] % p.G;
+            __half* orow = p.out + ((int64_t)tok[ri] * p.Hq + hq) * D;
+#pragma unroll
+            for (int db = 0; db < D / 8; ++db)
+                *reinterpret_cast<uint32_t*>(orow + db * 8 + t4 * 2) =
+                    pack_half2(o_acc[db][2 * ri] * inv, o_acc[db][2 * ri + 1] * inv);
+        }
+    } else {
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri) {
+            if (!row_ok[ri]) continue;
+            const int64_t grow = (int64_t)split * p.Hkv * rows_total + (int64_t)hkv * rows_total + row[ri];
+            float* orow = p.part_o + grow * D;
+#pragma unroll
+            for (int db = 0; db < D / 8; ++db)
+                *reinterpret_cast<float2*>(orow + db * 8 + t4 * 2) = make_float2(o_acc[db][2 * ri], o_acc[db][2 * ri + 1]);
+            if (t4 == 0) p.part_ml[grow] = make_float2(m_run[ri], l_run[ri]);
+        }
+    }
+}
+
+// grid (Hkv * qo * G); block D threads.  Merges the per-split (m, l, o) triples.
+template <int D>
+__global__ void __launch_bounds__(D) tree_attn_combine_kernel(const AttnParams p) {
+    const int rows_total = p.qo * p.G;
+    const int grow = blockIdx.x;                 // hkv * rows_total + row
+    const int hkv = grow / rows_total, row = grow % rows_total;
+    float m = -INFINITY;
+    for (int s = 0; s < p.splits; ++s) m = fmaxf(m, p.part_ml[(int64_t)s * p.Hkv * rows_total + grow].x);
+    const float m_use = m == -INFINITY ? 0.f : m;
+    float l = 0.f, o = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+        const int64_t idx = (int64_t)s * p.Hkv * rows_total + grow;
+        const float2 ml = p.part_ml[idx];
+        const float w = exp2f(ml.x - m_use);
+        l += ml.y * w;
+        o += p.part_o[idx * D + threadIdx.x] * w;
+    }
+    const int tok = row / p.G, hq = hkv * p.G + row % p.G;
+    p.out[((int64_t)tok * p.Hq + hq) * D + threadIdx.x] = __float2half_rn(l > 0.f ? o / l : 0.f);
+}
+
+static int choose_splits(int qo, int G, int Hkv, int kv_len) {
+    const int row_tiles = (qo * G + kBM - 1) / kBM;
+    const int kv_tiles = (kv_len + kBN - 1) / kBN;
+    const int base = row_tiles * Hkv;
+    int splits = (2 * sm_count() + base - 1) / base;      // aim at ~2 CTAs per SM
+    splits = splits < 1 ? 1 : splits;
+    const int max_by_len = (kv_tiles + 1) / 2;              // at least two kv tiles per split
+    splits = splits > max_by_len ? max_by_len : splits;
+    splits = splits > 64 ? 64 : splits;
+    return splits < 1 ? 1 : splits;
+}
+
+}  // namespace umb
+
+using namespace umb;
+
+extern "C" size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int head_dim, int max_kv_len) {
+    (void)max_kv_len;
+    if (qo < 1 || num_q_heads < 1 || head_dim < 1) return 0;
+    const size_t rows = (size_t)qo * num_q_heads;
+    return 64 * rows * ((size_t)head_dim * sizeof(float) + sizeof(float2)) + 256;
+}
+
+extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void* v_cache, void* out, int qo, int kv_len,
+                                 int num_q_heads, int num_kv_heads, int head_dim, int64_t kv_tok_stride,
+                                 int64_t kv_head_stride, const umb_attn_mask_t* mask, float sm_scale, float soft_cap,
+                                 void* workspace, size_t workspace_bytes, umb_stream_t stream) {
+    UMB_CHECK_ARG(q && k_cache && v_cache && out && mask);
+    UMB_CHECK_ARG(qo >= 1 && kv_len >= 1 && num_q_heads >= 1 && num_kv_heads >= 1);
+    UMB_CHECK_ARG(num_q_heads % num_kv_heads == 0);
+    UMB_CHECK_ARG((kv_tok_stride % 8) == 0 && (kv_head_stride % 8) == 0);
+    UMB_CHECK_ARG((((uintptr_t)q | (uintptr_t)k_cache | (uintptr_t)v_cache | (uintptr_t)out) & 15) == 0);
+    if (head_dim != 64 && head_dim != 128) return UMB_ERR_UNSUPPORTED;
+    if (mask->mask_mode == UMB_MASK_TREE) UMB_CHECK_ARG(mask->tree_bits && mask->tree_words * 32 >= qo);
+    if (mask->mask_mode == UMB_MASK_DENSE) UMB_CHECK_ARG(mask->dense_mask && mask->mask_stride >= kv_len);
+    UMB_CHECK_ARG(mask->mask_mode >= 0 && mask->mask_mode <= 2);
+
+    AttnParams p{};
+    p.q = (const __half*)q;
+    p.k = (const __half*)k_cache;
+    p.v = (const __half*)v_cache;
+    p.out = (__half*)out;
+    p.qo = qo;
+    p.kv_len = kv_len;
+    p.Hq = num_q_heads;
+    p.Hkv = num_kv_heads;
+    p.G = num_q_heads / num_kv_heads;
+    p.kv_tok_stride = kv_tok_stride;
+    p.kv_head_stride = kv_head_stride;
+    p.mask_mode = mask->mask_mode;
+    p.prefix_len = mask->prefix_len;
+    p.dyn = mask->dyn;
+    p.tree_bits = mask->tree_bits;
+    p.tree_words = mask->tree_words;
+    p.dense_mask = mask->dense_mask;
+    p.mask_stride = mask->mask_stride;
+    p.sm_scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)head_dim);
+    p.scale_log2 = p.sm_scale * 1.4426950408889634f;
+    p.soft_cap = soft_cap;
+    p.splits = choose_splits(qo, p.G, p.Hkv, kv_len);
+    const size_t rows = (size_t)qo * num_q_heads;
+    if (p.splits > 1) {
+        const size_t need = (size_t)p.splits * rows * ((size_t)head_dim * sizeof(float) + sizeof(float2)) + 256;
+        if (!workspace || workspace_bytes < need) {
+            // shrink to what fits (1 split needs no workspace)
+            size_t per = rows * ((size_t)head_dim * sizeof(float) + sizeof(float2));
+            int fit = workspace && workspace_bytes > 256 ? (int)((workspace_bytes - 256) / per) : 1;
+            p.splits = fit < 1 ? 1 : (fit < p.splits ? fit : p.splits);
+        }
+    }
+    if (p.splits > 1) {
+        uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+        p.part_o = reinterpret_cast<float*>(base);
+        p.part_ml = reinterpret_cast<float2*>(base + (size_t)p.splits * rows * head_dim * sizeof(float));
+    }
+    const dim3 grid((qo * p.G + kBM - 1) / kBM, p.Hkv, p.splits);
+    const size_t smem = (size_t)4 * kBN * head_dim * sizeof(__half);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (head_dim == 128) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            UMB_CUDA(cudaFuncSetAttribute(tree_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        tree_attn_kernel<128><<<grid, kAttnThreads, smem, st>>>(p);
+        if (p.splits > 1) tree_attn_combine_kernel<128><<<(unsigned)rows, 128, 0, st>>>(p);
+    } else {
+        tree_attn_kernel<64><<<grid, kAttnThreads, smem, st>>>(p);
+        if (p.splits > 1) tree_attn_combine_kernel<64><<<(unsigned)rows, 64, 0, st>>>(p);
+    }
+    count_launches(p.splits > 1 ? 2 : 1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}

@@ -7,11 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define UMB_OK 0
-#define UMB_ERR_ARG (-1)
-#define UMB_ERR_UNSUPPORTED (-2)
-#define UMB_ERR_WORKSPACE (-3)
-#define UMB_ERR_DRIVER (-4)
+#include "../../include/umbrella_b200.h"
 
 #define UMB_CHECK_ARG(cond) do { if (!(cond)) return UMB_ERR_ARG; } while (0)
 #define UMB_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)

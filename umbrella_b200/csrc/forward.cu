@@ -1,0 +1,113 @@
+// Native forward driver: enqueues the whole Llama verify forward from one C call (no Python between
+// kernels).  Mirrors LlamaAwq.inference / layer_compute (reference umbrella/models/llama.py:262-322)
+// and Llama.inference (llama.py:75-134) op for op; every fp16 rounding point of the reference is a
+// kernel boundary or an explicit rounding inside a fused epilogue here.
+#include "common.cuh"
+#include "internal.h"
+
+namespace umb {
+
+static int linear(const umb_llama_t* m, const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows,
+                  int K, int N, const umb_epilogue_t* epi, umb_stream_t st) {
+    if (m->awq)
+        return umb_awq_gemm_f16(x, ldx, w, y, ldy, rows, K, N, 128, epi, m->gemm_ws, m->gemm_ws_bytes, st);
+    return umb_gemm_f16(x, ldx, w, K, y, ldy, rows, K, N, epi, m->gemm_ws, m->gemm_ws_bytes, st);
+}
+
+#define UMB_TRY(expr) do { int rc__ = (expr); if (rc__ != UMB_OK) return rc__; } while (0)
+
+static int forward_chunk(const umb_llama_t* m, const int64_t* ids, const int64_t* pos, int rows, int kv_offset,
+                         const umb_attn_mask_t* mask, float* logits, int logits_from, unsigned long long* keys,
+                         umb_stream_t st) {
+    const int H = m->hidden_size, I = m->intermediate_size, Hq = m->num_q_heads, Hkv = m->num_kv_heads, D = m->head_dim;
+    const int qkv_n = (Hq + 2 * Hkv) * D;
+    const int64_t tok_stride = (int64_t)Hkv * D;
+    const int64_t layer_elems = (int64_t)m->max_length * tok_stride;
+    UMB_TRY(umb_embedding_f16(ids, m->embed, m->hidden, rows, H, st));
+    for (int l = 0; l < m->num_layers; ++l) {
+        const umb_llama_layer_t& L = m->layers[l];
+        __half* kc = (__half*)m->k_cache + l * layer_elems;
+        __half* vc = (__half*)m->v_cache + l * layer_elems;
+        UMB_TRY(umb_rmsnorm_f16(m->hidden, L.input_norm, m->normed, rows, H, m->rms_eps, st));
+        UMB_TRY(linear(m, m->normed, H, L.wqkv, m->qkv, qkv_n, rows, H, qkv_n, nullptr, st));
+        UMB_TRY(umb_rope_append_f16(m->qkv, qkv_n, m->q_rot, kc, vc, m->cos, m->sin, pos, rows, Hq, Hkv, D, tok_stride,
+                                    D, kv_offset, nullptr, st));
+        UMB_TRY(umb_tree_attn_f16(m->q_rot, kc, vc, m->attn_out, rows, kv_offset + rows, Hq, Hkv, D, tok_stride, D,
+                                  mask, 0.f, 0.f, m->attn_ws, m->attn_ws_bytes, st));
+        umb_epilogue_t res{};
+        res.mode = UMB_EPI_RESIDUAL;
+        res.residual = m->hidden;
+        res.ld_residual = H;
+        UMB_TRY(linear(m, m->attn_out, (int64_t)Hq * D, L.wo, m->hidden, H, rows, Hq * D, H, &res, st));
+        UMB_TRY(umb_rmsnorm_f16(m->hidden, L.post_norm, m->normed, rows, H, m->rms_eps, st));
+        umb_epilogue_t silu{};
+        silu.mode = UMB_EPI_SILU_MUL;
+        UMB_TRY(linear(m, m->normed, H, L.wgu, m->act, I, rows, H, 2 * I, &silu, st));
+        UMB_TRY(linear(m, m->act, I, L.wdown, m->hidden, H, rows, I, H, &res, st));
+    }
+    if (logits || keys) {
+        const int from = logits_from < 0 ? 0 : logits_from;
+        if (from < rows) {
+            const int n = rows - from;
+            UMB_TRY(umb_rmsnorm_f16((const __half*)m->hidden + (int64_t)from * H, m->final_norm, m->normed, n, H,
+                                    m->rms_eps, st));
+            umb_epilogue_t lg{};
+            lg.mode = UMB_EPI_LOGITS;
+            lg.argmax = keys;
+            // logits == NULL with keys only is not supported by the epilogue: the fp32 rows are always written
+            UMB_TRY(umb_gemm_f16(m->normed, H, m->lm_head, H, logits, m->vocab, n, H, m->vocab, &lg, m->gemm_ws,
+                                 m->gemm_ws_bytes, st));
+        }
+    }
+    return UMB_OK;
+}
+
+}  // namespace umb
+
+extern "C" size_t umb_llama_gemm_ws_bytes(int hidden, int intermediate, int num_q_heads, int num_kv_heads, int head_dim,
+                                          int vocab) {
+    size_t best = 0;
+    const int ns[5] = {(num_q_heads + 2 * num_kv_heads) * head_dim, hidden, 2 * intermediate, hidden, vocab};
+    for (int i = 0; i < 5; ++i) {
+        const size_t b = umb_gemm_workspace_bytes(128, hidden, ns[i]);
+        best = b > best ? b : best;
+    }
+    return best;
+}
+
+extern "C" int umb_llama_forward(const umb_llama_t* m, const int64_t* input_ids, const int64_t* position_ids, int rows,
+                                 int kv_offset, const umb_attn_mask_t* mask, float* logits, int logits_from_row,
+                                 unsigned long long* argmax_keys, umb_stream_t stream) {
+    UMB_CHECK_ARG(m && input_ids && position_ids && mask && rows >= 1 && kv_offset >= 0);
+    UMB_CHECK_ARG(m->layers && m->embed && m->final_norm && m->cos && m->sin && m->k_cache && m->v_cache);
+    UMB_CHECK_ARG(m->hidden && m->normed && m->qkv && m->q_rot && m->attn_out && m->act && m->gemm_ws);
+    UMB_CHECK_ARG(kv_offset + rows <= m->max_length);
+    UMB_CHECK_ARG(!argmax_keys || logits);
+    if (logits) UMB_CHECK_ARG(m->lm_head != nullptr);
+    const int chunk = 128;
+    for (int r0 = 0; r0 < rows; r0 += chunk) {
+        const int n = rows - r0 < chunk ? rows - r0 : chunk;
+        umb_attn_mask_t mk = *mask;
+        if (mk.mask_mode == UMB_MASK_DENSE) {
+            mk.dense_mask = mask->dense_mask + (int64_t)r0 * mask->mask_stride;
+        } else if (mk.mask_mode == UMB_MASK_CAUSAL) {
+            mk.prefix_len = mask->prefix_len + r0;
+        } else if (rows > chunk) {
+            return UMB_ERR_UNSUPPORTED;   // a token tree larger than 128 rows goes through the dense form
+        }
+        // logits rows of this chunk
+        float* lg = nullptr;
+        unsigned long long* keys = nullptr;
+        int from = 0;
+        if (logits && logits_from_row < r0 + n) {
+            from = logits_from_row > r0 ? logits_from_row - r0 : 0;
+            const int64_t out_row = (int64_t)(r0 + from) - logits_from_row;
+            lg = logits + out_row * m->vocab;
+            keys = argmax_keys ? argmax_keys + out_row : nullptr;
+        }
+        const int rc = umb::forward_chunk(m, input_ids + r0, position_ids + r0, n, kv_offset + r0, &mk, lg, from, keys,
+                                          stream);
+        if (rc != UMB_OK) return rc;
+    }
+    return UMB_OK;
+}

@@ -1,0 +1,809 @@
+// (i) AWQ INT4 weight-dequant fused into a tcgen05 tensor-core GEMM, plus its fp16-weight twin.
+//
+// Replaces awq_ext.gemm_forward_cuda / dequantize_weights_cuda as called from AwqLinear.apply
+// (reference umbrella/quantization/awq_utils.py:63-86) and torch F.linear for fp16 weights
+// (lm_head: umbrella/models/llama.py:321; fp16 models: llama.py:87-110).
+//
+// Orientation ("swap-AB"): the verify pass multiplies M <= 128 token rows by a huge weight matrix,
+// so the WEIGHTS are the UMMA A operand (128 output features per tile = the 128 TMEM lanes) and the
+// token rows are the UMMA B/N operand (N = M padded to 16/32/64/128):
+//     D[128 features, MPAD tokens] (fp32, TMEM) += A[128, k] * B[MPAD, k]^T .
+// Every weight byte is read from HBM exactly once per call.
+//
+// AWQ mainloop (per 128-feature x 128-k "unit" = one 8512-byte record of the repacked stream):
+//   warp 0      TMA producer: cp.async.bulk of the packed record + cp.async.bulk.tensor (SW128)
+//               of the x slab [MPAD, 128 k] into a kStages-deep shared-memory ring
+//   warps 2..9  dequant: thread = one feature row x 64 k; lop3 nibble -> fp16 (1024+q), exact
+//               hsub2 of (1024+z), one hmul2 by the group scale == fp16((q - z) * s), the same
+//               rounding as the reference kernels; the fp16 row goes straight to TENSOR MEMORY
+//               with tcgen05.st (no shared-memory round trip, no swizzle arithmetic)
+//   warp 1      one thread issues tcgen05.mma kind::f16 with A from TMEM, B from shared memory
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator, fuse bias / residual / SiLU*up / fp32
+//               logits, fp16 rounding placed where the reference has fp16 tensors
+// Work is distributed stream-K: the (tile, k-group) space is cut into gridDim.x equal contiguous
+// ranges (one persistent CTA per SM), partial tiles are reduced through a small fp32 workspace in a
+// fixed order by the last-arriving CTA, so results are deterministic.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace umb {
+
+constexpr int kTileN = 128;              // output features per tile (UMMA M)
+constexpr int kGroup = 128;              // AWQ group size == k per AWQ unit
+constexpr int kRecordBytes = 8512;       // 8192 nibble bytes + 256 scale bytes + 64 zero bytes
+constexpr int kRecScaleOff = 8192;
+constexpr int kRecZeroOff = 8448;
+constexpr int kGemmThreads = 320;        // 10 warps
+constexpr int kTmemCols = 512;
+constexpr int kTmemAStages = 4;          // 4 x 64 columns of fp16 A operand
+constexpr int kTmemACol0 = 128;
+
+// nibble position of the i-th of 8 consecutive values inside a 32-bit word: (0,4,1,5,2,6,3,7).
+// Used by the AutoAWQ checkpoint layout (along N) and by our repacked stream (along K): nibbles p
+// and p + 4 hold consecutive values, so (w >> 4p) & 0x000f000f yields an ordered pair.
+__host__ __device__ __forceinline__ int nib_pos(int i) { return (i >> 1) + ((i & 1) << 2); }
+
+// ------------------------------------------------------------------------------------------------
+// repack / dequantize / unpack
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t packed_row(int n, int row_block, int row_stride, int row_offset) {
+    return (int64_t)(n / row_block) * row_stride + row_offset + n % row_block;
+}
+
+// thread (kw, c): 8 k x 8 n block of the checkpoint -> 8 words (one per n) of 8 k-nibbles
+__global__ void awq_repack_weights_kernel(const int32_t* __restrict__ qweight, int K, int N, unsigned char* packed,
+                                          int row_block, int row_stride, int row_offset) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kw = blockIdx.y;
+    if (c >= N / 8) return;
+    uint32_t in[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) in[i] = (uint32_t)qweight[(int64_t)(kw * 8 + i) * (N / 8) + c];
+    const int k0 = kw * 8, g = k0 / kGroup, kk = k0 % kGroup;
+    const int kb = kk >> 6, ch = (kk >> 5) & 1, w = (kk >> 3) & 3;
+    const int G = K / kGroup;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out |= ((in[i] >> (4 * nib_pos(j))) & 0xFu) << (4 * nib_pos(i));
+        const int64_t pr = packed_row(c * 8 + j, row_block, row_stride, row_offset);
+        const int64_t tile = pr / kTileN;
+        const int r = (int)(pr % kTileN);
+        unsigned char* rec = packed + (tile * G + g) * kRecordBytes;
+        *reinterpret_cast<uint32_t*>(rec + ((kb * 2 + ch) * kTileN + r) * 16 + w * 4) = out;
+    }
+}
+// thread (g, c): scales and zeros of 8 consecutive output features of one group
+__global__ void awq_repack_meta_kernel(const int32_t* __restrict__ qzeros, const __half* __restrict__ scales, int K,
+                                       int N, unsigned char* packed, int row_block, int row_stride, int row_offset) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (c >= N / 8) return;
+    const int G = K / kGroup;
+    const uint32_t zin = (uint32_t)qzeros[(int64_t)g * (N / 8) + c];
+    uint32_t zout = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) zout |= ((zin >> (4 * nib_pos(j))) & 0xFu) << (4 * j);
+    const int64_t pr = packed_row(c * 8, row_block, row_stride, row_offset);   // 8-aligned run of rows
+    const int64_t tile = pr / kTileN;
+    const int r = (int)(pr % kTileN);
+    unsigned char* rec = packed + (tile * G + g) * kRecordBytes;
+    *reinterpret_cast<uint32_t*>(rec + kRecZeroOff + (r >> 3) * 4) = zout;
+    *reinterpret_cast<uint4*>(rec + kRecScaleOff + r * 2) =
+        *reinterpret_cast<const uint4*>(scales + (int64_t)g * N + c * 8);
+}
+
+// awq_ext.dequantize_weights_cuda: out[k, n] = fp16((q - z) * s), checkpoint layout in, [K, N] out
+__global__ void awq_dequantize_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
+                                      const __half* __restrict__ scales, int K, int N, __half* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (c >= N / 8) return;
+    const uint32_t q = (uint32_t)qweight[(int64_t)k * (N / 8) + c];
+    const uint32_t z = (uint32_t)qzeros[(int64_t)(k / kGroup) * (N / 8) + c];
+    union { uint4 u; __half h[8]; } s, o;
+    s.u = *reinterpret_cast<const uint4*>(scales + (int64_t)(k / kGroup) * N + c * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = (int)((q >> (4 * nib_pos(j))) & 0xFu) - (int)((z >> (4 * nib_pos(j))) & 0xFu);
+        o.h[j] = __hmul(__int2half_rn(d), s.h[j]);
+    }
+    *reinterpret_cast<uint4*>(out + (int64_t)k * N + c * 8) = o.u;
+}
+
+// packed stream -> fp16 [N_total, K]  (row = packed row); thread = (row, 8 k)
+__global__ void awq_unpack_kernel(const unsigned char* __restrict__ packed, int K, int N_total,
+                                  __half* __restrict__ out) {
+    const int kw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pr = blockIdx.y;
+    if (kw >= K / 8) return;
+    const int G = K / kGroup;
+    const int k0 = kw * 8, g = k0 / kGroup, kk = k0 % kGroup;
+    const int kb = kk >> 6, ch = (kk >> 5) & 1, w = (kk >> 3) & 3;
+    const int tile = pr / kTileN, r = pr % kTileN;
+    const unsigned char* rec = packed + ((int64_t)tile * G + g) * kRecordBytes;
+    const uint32_t word = *reinterpret_cast<const uint32_t*>(rec + ((kb * 2 + ch) * kTileN + r) * 16 + w * 4);
+    const uint32_t zw = *reinterpret_cast<const uint32_t*>(rec + kRecZeroOff + (r >> 3) * 4);
+    const int z = (int)((zw >> (4 * (r & 7))) & 0xFu);
+    const __half s = *reinterpret_cast<const __half*>(rec + kRecScaleOff + r * 2);
+    union { uint4 u; __half h[8]; } o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.h[i] = __hmul(__int2half_rn((int)((word >> (4 * nib_pos(i))) & 0xFu) - z), s);
+    *reinterpret_cast<uint4*>(out + (int64_t)pr * K + k0) = o.u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream-K schedule helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long sk_begin(long long c, long long U, long long P) { return c * U / P; }
+__device__ __forceinline__ int sk_owner(long long u, long long U, long long P) {
+    long long c = u * P / U;
+    while (c + 1 < P && sk_begin(c + 1, U, P) <= u) ++c;
+    while (c > 0 && sk_begin(c, U, P) > u) --c;
+    return (int)c;
+}
+
+struct GemmParams {
+    const unsigned char* packed;   // AWQ stream (kAwq) -- else unused
+    int M, K, N_total;             // N_total = output features (rows of W)
+    int units_per_tile;            // K / 128 (AWQ) or K / 64 (fp16)
+    int tiles;
+    void* y;
+    int64_t ldy;
+    int mode;
+    const __half* bias;
+    const __half* residual;
+    int64_t ld_residual;
+    unsigned long long* argmax;
+    int* counters;                 // [tiles]
+    float* slots;                  // [tiles + grid][MPAD][128]
+};
+
+template <int MPAD>
+struct GemmCfg {
+    static constexpr int kStagesAwq = MPAD <= 32 ? 8 : (MPAD == 64 ? 6 : 4);
+    static constexpr int kStagesF16 = MPAD <= 32 ? 8 : (MPAD == 64 ? 6 : 4);
+    static constexpr int kXBytesAwq = MPAD * 256;           // [2 atoms][MPAD][128 B]
+    static constexpr int kXBytesF16 = MPAD * 128;           // [MPAD][128 B]
+    static constexpr int kWBytesF16 = kTileN * 128;         // [128][128 B]
+    static constexpr int kPackedStride = 8576;              // record padded to a 128-byte multiple
+    static constexpr int kExchBytes = MPAD * 64 * 2;
+    static constexpr int kBarBytes = 512;
+    static constexpr int smem_bytes(bool awq) {
+        return 1024 /*align slack*/ + kBarBytes + kExchBytes +
+               (awq ? kStagesAwq * (kXBytesAwq + kPackedStride) : kStagesF16 * (kXBytesF16 + kWBytesF16));
+    }
+};
+
+__device__ __forceinline__ float silu_f(float f) { return f / (1.f + expf(-f)); }
+__device__ __forceinline__ unsigned int orderable_f32_g(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Epilogue of 16 token columns [m0, m0 + 16) for feature lane `fl` (0..127) of tile `tile`.
+template <int MPAD>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, int fl, int m0, const float (&v)[16],
+                                               __half* exch) {
+    const int n = tile * kTileN + fl;
+    if (p.mode == UMB_EPI_SILU_MUL) {
+        // lanes 64..127 hold `up`, lanes 0..63 hold `gate` of output feature tile*64 + (fl & 63)
+        if (fl >= 64) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) exch[(m0 + j) * 64 + (fl - 64)] = __float2half_rn(v[j]);
+        }
+        named_bar_sync(2, 128);
+        if (fl < 64) {
+            const int no = tile * 64 + fl;
+            if (no < p.N_total / 2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int m = m0 + j;
+                    if (m < p.M) {
+                        const __half g = __float2half_rn(v[j]);
+                        const __half s = __float2half_rn(silu_f(__half2float(g)));
+                        reinterpret_cast<__half*>(p.y)[(int64_t)m * p.ldy + no] = __hmul(s, exch[m * 64 + fl]);
+                    }
+                }
+            }
+        }
+        named_bar_sync(2, 128);
+        return;
+    }
+    const bool n_ok = n < p.N_total;
+    if (!n_ok && !(p.mode == UMB_EPI_LOGITS && p.argmax)) return;
+    const __half b = (p.bias && n_ok) ? p.bias[n] : __float2half_rn(0.f);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int m = m0 + j;
+        if (m >= p.M) break;
+        __half h = __float2half_rn(v[j]);
+        if (p.bias) h = __hadd(h, b);
+        if (p.mode == UMB_EPI_RESIDUAL) {
+            h = __hadd(p.residual[(int64_t)m * p.ld_residual + n], h);
+            reinterpret_cast<__half*>(p.y)[(int64_t)m * p.ldy + n] = h;
+        } else if (p.mode == UMB_EPI_LOGITS) {
+            const float f = __half2float(h);
+            if (n_ok) reinterpret_cast<float*>(p.y)[(int64_t)m * p.ldy + n] = f;
+            if (p.argmax) {
+                // warp-level max first: one atomic per (warp, token)
+                unsigned long long key =
+                    n_ok ? (((unsigned long long)orderable_f32_g(f) << 32) | (unsigned int)(~n)) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other > key ? other : key;
+                }
+                if ((threadIdx.x & 31) == 0) atomicMax(p.argmax + m, key);
+            }
+        } else {
+            reinterpret_cast<__half*>(p.y)[(int64_t)m * p.ldy + n] = h;
+        }
+    }
+}
+
+template <int MPAD, bool kAwq>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+            const GemmParams p) {
+    using Cfg = GemmCfg<MPAD>;
+    constexpr int kStages = kAwq ? Cfg::kStagesAwq : Cfg::kStagesF16;
+    constexpr int kXBytes = kAwq ? Cfg::kXBytesAwq : Cfg::kXBytesF16;
+    constexpr int kWStride = kAwq ? Cfg::kPackedStride : Cfg::kWBytesF16;
+    constexpr uint32_t kTxBytes = kAwq ? (uint32_t)(kRecordBytes + kXBytes) : (uint32_t)(Cfg::kWBytesF16 + kXBytes);
+    constexpr uint32_t kIdesc = umma_idesc_f16(kTileN, MPAD);
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* s_x = smem;                                   // kStages x kXBytes   (1024-aligned slabs)
+    unsigned char* s_w = s_x + kStages * kXBytes;                // kStages x kWStride
+    __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStride);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes);
+    uint64_t* full = bars;                    // [kStages]
+    uint64_t* empty = bars + 8;               // [kStages]
+    uint64_t* a_full = bars + 16;             // [kTmemAStages]
+    uint64_t* a_empty = bars + 20;            // [kTmemAStages]
+    uint64_t* acc_full = bars + 24;
+    uint64_t* acc_empty = bars + 25;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 26);
+    int* s_flag = reinterpret_cast<int*>(bars + 27);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long U = (long long)p.tiles * p.units_per_tile, P = gridDim.x;
+    const long long u_begin = sk_begin(blockIdx.x, U, P), u_end = sk_begin(blockIdx.x + 1, U, P);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        if (!kAwq) tma_prefetch_desc(&tmap_w);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, kAwq ? 9 : 1);
+        }
+        for (int i = 0; i < kTmemAStages; ++i) {
+            mbar_init(a_full + i, 8);
+            mbar_init(a_empty + i, 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(s_tmem, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
+            Ring r;
+            for (long long u = u_begin; u < u_end; ++u) {
+                const int tile = (int)(u / p.units_per_tile), g = (int)(u % p.units_per_tile);
+                mbar_wait(empty + r.stage, r.phase ^ 1);
+                mbar_arrive_expect_tx(full + r.stage, kTxBytes);
+                unsigned char* xs = s_x + r.stage * kXBytes;
+                if constexpr (kAwq) {
+                    tma_bulk_g2s(s_w + r.stage * kWStride, p.packed + u * kRecordBytes, kRecordBytes, full + r.stage, pol_w);
+                    tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full + r.stage, pol_x);
+                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full + r.stage, pol_x);
+                } else {
+                    tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full + r.stage, pol_w);
+                    tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full + r.stage, pol_x);
+                }
+                r.advance(kStages);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            Ring r, ra;
+            int seg = 0;
+            long long u = u_begin;
+            while (u < u_end) {
+                const int tile = (int)(u / p.units_per_tile);
+                const long long seg_end = min(u_end, (long long)(tile + 1) * p.units_per_tile);
+                mbar_wait(acc_empty, (seg & 1) ^ 1);
+                tc_fence_after();
+                bool first = true;
+                for (; u < seg_end; ++u) {
+                    mbar_wait(full + r.stage, r.phase);
+                    const uint32_t xs = smem_u32(s_x + r.stage * kXBytes);
+                    if constexpr (kAwq) {
+                        mbar_wait(a_full + ra.stage, ra.phase);
+                        tc_fence_after();
+                        const uint32_t a_col = tmem_base + kTmemACol0 + ra.stage * 64;
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint64_t bd = umma_smem_desc_sw128(xs + (kk >> 2) * (MPAD * 128) + (kk & 3) * 32);
+                            umma_ts_f16(tmem_base, a_col + kk * 8, bd, kIdesc, (first && kk == 0) ? 0u : 1u);
+                        }
+                        umma_commit(a_empty + ra.stage);
+                        ra.advance(kTmemAStages);
+                    } else {
+                        tc_fence_after();
+                        const uint32_t ws = smem_u32(s_w + r.stage * kWStride);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t ad = umma_smem_desc_sw128(ws + kk * 32);
+                            const uint64_t bd = umma_smem_desc_sw128(xs + kk * 32);
+                            umma_ss_f16(tmem_base, ad, bd, kIdesc, (first && kk == 0) ? 0u : 1u);
+                        }
+                    }
+                    umma_commit(empty + r.stage);
+                    first = false;
+                    r.advance(kStages);
+                }
+                umma_commit(acc_full);
+                ++seg;
+            }
+        }
+    } else {
+        // ===================== dequant (AWQ) + epilogue warps =====================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may touch
+        const int khalf = (warp - 2) >> 2;           // 0: warps 2..5, 1: warps 6..9
+        const bool is_epi = warp < 6;
+        const int fl = q * 32 + lane;                // feature lane 0..127
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        Ring r, ra;
+        int seg = 0;
+        long long u = u_begin;
+        while (u < u_end) {
+            const int tile = (int)(u / p.units_per_tile);
+            const long long tile_u0 = (long long)tile * p.units_per_tile;
+            const long long seg_begin = u;
+            const long long seg_end = min(u_end, tile_u0 + p.units_per_tile);
+            if constexpr (kAwq) {
+                for (; u < seg_end; ++u) {
+                    mbar_wait(full + r.stage, r.phase);
+                    const unsigned char* rec = s_w + r.stage * kWStride;
+                    const uint4 w0 = *reinterpret_cast<const uint4*>(rec + ((khalf * 2 + 0) * kTileN + fl) * 16);
+                    const uint4 w1 = *reinterpret_cast<const uint4*>(rec + ((khalf * 2 + 1) * kTileN + fl) * 16);
+                    const uint32_t sbits = *reinterpret_cast<const unsigned short*>(rec + kRecScaleOff + fl * 2);
+                    const uint32_t zw = *reinterpret_cast<const uint32_t*>(rec + kRecZeroOff + (fl >> 3) * 4);
+                    const uint32_t zh = 0x6400u | ((zw >> (4 * (fl & 7))) & 0xFu);      // fp16(1024 + z)
+                    const uint32_t z2u = zh | (zh << 16), s2u = sbits | (sbits << 16);
+                    const __half2 z2 = *reinterpret_cast<const __half2*>(&z2u);
+                    const __half2 s2 = *reinterpret_cast<const __half2*>(&s2u);
+                    uint32_t a[32];
+                    const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+#pragma unroll
+                        for (int pp = 0; pp < 4; ++pp) {
+                            uint32_t t = ((words[w] >> (4 * pp)) & 0x000f000fu) | 0x64006400u;   // (1024+q_lo, 1024+q_hi)
+                            __half2 h = __hsub2(*reinterpret_cast<__half2*>(&t), z2);              // exact q - z
+                            h = __hmul2(h, s2);                                                    // one rounding
+                            a[w * 4 + pp] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                    }
+                    mbar_wait(a_empty + ra.stage, ra.phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + lane_addr + kTmemACol0 + ra.stage * 64 + khalf * 32;
+                    UMB_TMEM_ST_X16(taddr, (&a[0]));
+                    UMB_TMEM_ST_X16(taddr + 16, (&a[16]));
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(a_full + ra.stage);
+                        mbar_arrive(empty + r.stage);
+                    }
+                    r.advance(kStages);
+                    ra.advance(kTmemAStages);
+                }
+            } else {
+                u = seg_end;
+            }
+            if (is_epi) {
+                const bool whole = (seg_begin == tile_u0) && (seg_end == tile_u0 + p.units_per_tile);
+                mbar_wait(acc_full, seg & 1);
+                tc_fence_after();
+                if (whole) {
+#pragma unroll 1
+                    for (int m0 = 0; m0 < MPAD; m0 += 16) {
+                        uint32_t rr[16];
+                        UMB_TMEM_LD_X16(tmem_base + lane_addr + m0, rr);
+                        tc_wait_ld();
+                        if (m0 + 16 >= MPAD) {       // accumulator fully read: hand TMEM back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(acc_empty);
+                        }
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+                        if (m0 < p.M || p.mode == UMB_EPI_SILU_MUL) epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
+                    }
+                } else {
+                    // partial tile: publish to this CTA's slot, the last arriver reduces in slot order
+                    float* slot = p.slots + ((size_t)tile + blockIdx.x) * (MPAD * kTileN);
+#pragma unroll 1
+                    for (int m0 = 0; m0 < MPAD; m0 += 16) {
+                        uint32_t rr[16];
+                        UMB_TMEM_LD_X16(tmem_base + lane_addr + m0, rr);
+                        tc_wait_ld();
+                        if (m0 + 16 >= MPAD) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(acc_empty);
+                        }
+                        if (m0 < p.M) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) slot[(m0 + j) * kTileN + fl] = __uint_as_float(rr[j]);
+                        }
+                    }
+                    __threadfence();
+                    named_bar_sync(1, 128);
+                    const int c_first = sk_owner(tile_u0, U, P);
+                    const int c_last = sk_owner(tile_u0 + p.units_per_tile - 1, U, P);
+                    if (warp == 2 && lane == 0) {
+                        const int old = atomicAdd(p.counters + tile, 1);
+                        const int last = (old == c_last - c_first) ? 1 : 0;
+                        if (last) p.counters[tile] = 0;
+                        *s_flag = last;
+                    }
+                    named_bar_sync(1, 128);
+                    const bool is_last = *s_flag != 0;
+                    named_bar_sync(1, 128);          // s_flag may be rewritten by the next segment
+                    if (is_last) {
+                        __threadfence();
+#pragma unroll 1
+                        for (int m0 = 0; m0 < MPAD; m0 += 16) {
+                            if (!(m0 < p.M || p.mode == UMB_EPI_SILU_MUL)) break;
+                            float v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                            if (m0 < p.M) {
+                                for (int c = c_first; c <= c_last; ++c) {
+                                    const float* sl = p.slots + ((size_t)tile + c) * (MPAD * kTileN);
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[j] += ld_cg_f32(sl + (m0 + j) * kTileN + fl);
+                                }
+                            }
+                            epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
+                        }
+                    }
+                }
+            }
+            ++seg;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe: one 128 x 16 x 64 UMMA, A from shared memory (mode 0) or tensor memory (mode 1)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+probe_umma_kernel(const __half* __restrict__ a, const __half* __restrict__ b, float* __restrict__ d, int mode) {
+    __shared__ __align__(1024) unsigned char s_a[128 * 128];
+    __shared__ __align__(1024) unsigned char s_b[16 * 128];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = threadIdx.x;
+    // manual SW128 K-major tiles: element (row, k) at (row/8)*1024 + (row%8)*128 + ((k/8) ^ (row%8))*16 + (k%8)*2
+    for (int c = 0; c < 8; ++c) {
+        const uint4 va = *reinterpret_cast<const uint4*>(a + r * 64 + c * 8);
+        *reinterpret_cast<uint4*>(s_a + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = va;
+        if (r < 16) {
+            const uint4 vb = *reinterpret_cast<const uint4*>(b + r * 64 + c * 8);
+            *reinterpret_cast<uint4*>(s_b + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = vb;
+        }
+    }
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&s_tmem, 64);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    if (mode == 1) {
+        uint32_t regs[32];
+        for (int c = 0; c < 32; ++c) regs[c] = *reinterpret_cast<const uint32_t*>(a + r * 64 + c * 2);
+        UMB_TMEM_ST_X16(tmem + lane_addr + 32, (&regs[0]));
+        UMB_TMEM_ST_X16(tmem + lane_addr + 48, (&regs[16]));
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = umma_idesc_f16(128, 16);
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bd = umma_smem_desc_sw128(smem_u32(s_b) + kk * 32);
+            if (mode == 1) {
+                umma_ts_f16(tmem, tmem + 32 + kk * 8, bd, idesc, kk ? 1u : 0u);
+            } else {
+                const uint64_t ad = umma_smem_desc_sw128(smem_u32(s_a) + kk * 32);
+                umma_ss_f16(tmem, ad, bd, idesc, kk ? 1u : 0u);
+            }
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    uint32_t rr[16];
+    UMB_TMEM_LD_X16(tmem + lane_addr, rr);
+    tc_wait_ld();
+    for (int j = 0; j < 16; ++j) d[r * 16 + j] = __uint_as_float(rr[j]);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 64);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-check of the packed stream (tests only): one CTA per tile, thread = feature row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+awq_gemm_simt_kernel(const unsigned char* __restrict__ packed, const __half* __restrict__ x, int64_t ldx,
+                     __half* __restrict__ y, int64_t ldy, int M, int K, int N_total) {
+    const int tile = blockIdx.x, r = threadIdx.x, G = K / kGroup;
+    const int n = tile * kTileN + r;
+    for (int m0 = 0; m0 < M; m0 += 8) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int g = 0; g < G; ++g) {
+            const unsigned char* rec = packed + ((int64_t)tile * G + g) * kRecordBytes;
+            const uint32_t zw = *reinterpret_cast<const uint32_t*>(rec + kRecZeroOff + (r >> 3) * 4);
+            const int z = (int)((zw >> (4 * (r & 7))) & 0xFu);
+            const __half s = *reinterpret_cast<const __half*>(rec + kRecScaleOff + r * 2);
+            for (int c = 0; c < 4; ++c) {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(rec + (c * kTileN + r) * 16);
+                const uint32_t words[4] = {w4.x, w4.y, w4.z, w4.w};
+                for (int w = 0; w < 4; ++w)
+                    for (int i = 0; i < 8; ++i) {
+                        const float wf = __half2float(__hmul(__int2half_rn((int)((words[w] >> (4 * nib_pos(i))) & 0xFu) - z), s));
+                        const int k = g * kGroup + c * 32 + w * 8 + i;
+                        for (int j = 0; j < 8; ++j)
+                            if (m0 + j < M) acc[j] = fmaf(__half2float(x[(int64_t)(m0 + j) * ldx + k]), wf, acc[j]);
+                    }
+            }
+        }
+        if (n < N_total)
+            for (int j = 0; j < 8; ++j)
+                if (m0 + j < M) y[(int64_t)(m0 + j) * ldy + n] = __float2half_rn(acc[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(sym);
+    }
+    return fn;
+}
+// fp16 row-major [rows, cols] (leading dimension ld elements) -> tiled map, box [64 cols, box_rows], SW128
+static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return UMB_ERR_DRIVER;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * sizeof(__half)};
+    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? UMB_OK : UMB_ERR_ARG;
+}
+
+static int mpad_of(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128)); }
+
+template <int MPAD, bool kAwq>
+static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmParams& p, int grid, cudaStream_t st) {
+    const int smem = GemmCfg<MPAD>::smem_bytes(kAwq);
+    static bool attr_done = false;
+    if (!attr_done) {
+        UMB_CUDA(cudaFuncSetAttribute(gemm_kernel<MPAD, kAwq>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    gemm_kernel<MPAD, kAwq><<<grid, kGemmThreads, smem, st>>>(tx, tw, p);
+    count_launches(1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
+
+static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int64_t ldw, void* y, int64_t ldy, int M,
+                       int K, int N_total, const umb_epilogue_t* epi, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st) {
+    UMB_CHECK_ARG(x && w && y && M >= 1 && K >= 1 && N_total >= 1);
+    UMB_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0 && (ldx % 8) == 0 && ldx >= K);
+    if (M > 128) return UMB_ERR_UNSUPPORTED;
+    if (awq ? (K % kGroup) != 0 : (K % 64) != 0) return UMB_ERR_UNSUPPORTED;
+    if (N_total % 8) return UMB_ERR_UNSUPPORTED;
+    GemmParams p{};
+    p.packed = awq ? (const unsigned char*)w : nullptr;
+    p.M = M;
+    p.K = K;
+    p.N_total = N_total;
+    p.units_per_tile = awq ? K / kGroup : K / 64;
+    p.tiles = (N_total + kTileN - 1) / kTileN;
+    p.y = y;
+    p.ldy = ldy;
+    p.mode = epi ? epi->mode : UMB_EPI_STORE;
+    p.bias = epi ? (const __half*)epi->bias : nullptr;
+    p.residual = epi ? (const __half*)epi->residual : nullptr;
+    p.ld_residual = epi ? epi->ld_residual : 0;
+    p.argmax = epi ? epi->argmax : nullptr;
+    UMB_CHECK_ARG(p.mode >= UMB_EPI_STORE && p.mode <= UMB_EPI_LOGITS);
+    if (p.mode == UMB_EPI_RESIDUAL) UMB_CHECK_ARG(p.residual != nullptr);
+    if (p.mode == UMB_EPI_SILU_MUL) UMB_CHECK_ARG((N_total % kTileN) == 0 && p.bias == nullptr);
+
+    const int mpad = mpad_of(M);
+    const long long U = (long long)p.tiles * p.units_per_tile;
+    int grid = sm_count();
+    if ((long long)grid > U) grid = (int)U;
+    const size_t need = umb_gemm_workspace_bytes(M, K, N_total);
+    if (!workspace || workspace_bytes < need) return UMB_ERR_WORKSPACE;
+    UMB_CHECK_ARG(((uintptr_t)workspace & 15) == 0);
+    p.counters = reinterpret_cast<int*>(workspace);
+    p.slots = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (((size_t)p.tiles * 4 + 255) & ~(size_t)255));
+
+    CUtensorMap tx, tw;
+    int rc = make_tmap(&tx, x, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)mpad);
+    if (rc != UMB_OK) return rc;
+    if (!awq) {
+        UMB_CHECK_ARG((ldw % 8) == 0 && ldw >= K);
+        rc = make_tmap(&tw, w, (uint64_t)N_total, (uint64_t)K, (uint64_t)ldw, (uint32_t)kTileN);
+        if (rc != UMB_OK) return rc;
+    } else {
+        tw = tx;
+    }
+#define UMB_DISPATCH(MP)                                                       \
+    return awq ? launch_gemm<MP, true>(tx, tw, p, grid, st) : launch_gemm<MP, false>(tx, tw, p, grid, st)
+    switch (mpad) {
+        case 16: UMB_DISPATCH(16);
+        case 32: UMB_DISPATCH(32);
+        case 64: UMB_DISPATCH(64);
+        default: UMB_DISPATCH(128);
+    }
+#undef UMB_DISPATCH
+}
+
+}  // namespace umb
+
+using namespace umb;
+
+extern "C" size_t umb_awq_packed_bytes(int K, int N_total, int group) {
+    if (group != kGroup || K <= 0 || N_total <= 0 || (K % kGroup) != 0) return 0;
+    return (size_t)((N_total + kTileN - 1) / kTileN) * (K / kGroup) * kRecordBytes;
+}
+
+extern "C" size_t umb_gemm_workspace_bytes(int M, int K, int N_total) {
+    (void)K;
+    if (M < 1 || N_total < 1) return 0;
+    const size_t tiles = (size_t)(N_total + kTileN - 1) / kTileN;
+    const size_t mpad = (size_t)mpad_of(M > 128 ? 128 : M);
+    const size_t slots = tiles + 1024;   // tiles + an upper bound on the grid size
+    return ((tiles * 4 + 255) & ~(size_t)255) + slots * mpad * kTileN * sizeof(float);
+}
+
+extern "C" int umb_awq_repack(const int32_t* qweight, const int32_t* qzeros, const void* scales, int K, int N, int group,
+                              void* packed, int N_total, int row_block, int row_stride, int row_offset,
+                              umb_stream_t stream) {
+    UMB_CHECK_ARG(qweight && qzeros && scales && packed);
+    if (group != kGroup) return UMB_ERR_UNSUPPORTED;
+    UMB_CHECK_ARG(K > 0 && N > 0 && (K % kGroup) == 0 && (N % 8) == 0);
+    UMB_CHECK_ARG(row_block > 0 && (row_block % 8) == 0 && (row_offset % 8) == 0 && (row_stride % 8) == 0);
+    UMB_CHECK_ARG((N % row_block) == 0 || N < row_block);
+    const int64_t last = (int64_t)((N - 1) / row_block) * row_stride + row_offset + (N - 1) % row_block;
+    UMB_CHECK_ARG(last < (int64_t)((N_total + kTileN - 1) / kTileN) * kTileN);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cols = N / 8;
+    awq_repack_weights_kernel<<<dim3((cols + 127) / 128, K / 8), 128, 0, st>>>(qweight, K, N, (unsigned char*)packed,
+                                                                                row_block, row_stride, row_offset);
+    awq_repack_meta_kernel<<<dim3((cols + 127) / 128, K / kGroup), 128, 0, st>>>(
+        qzeros, (const __half*)scales, K, N, (unsigned char*)packed, row_block, row_stride, row_offset);
+    count_launches(2);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
+
+extern "C" int umb_awq_dequantize_f16(const int32_t* qweight, const int32_t* qzeros, const void* scales, int K, int N,
+                                      int group, void* out, umb_stream_t stream) {
+    UMB_CHECK_ARG(qweight && qzeros && scales && out);
+    if (group != kGroup) return UMB_ERR_UNSUPPORTED;
+    UMB_CHECK_ARG(K > 0 && N > 0 && (K % kGroup) == 0 && (N % 8) == 0);
+    awq_dequantize_kernel<<<dim3((N / 8 + 127) / 128, K), 128, 0, (cudaStream_t)stream>>>(
+        qweight, qzeros, (const __half*)scales, K, N, (__half*)out);
+    count_launches(1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
+
+extern "C" int umb_awq_unpack_f16(const void* packed, int K, int N_total, int group, void* out, umb_stream_t stream) {
+    UMB_CHECK_ARG(packed && out);
+    if (group != kGroup) return UMB_ERR_UNSUPPORTED;
+    UMB_CHECK_ARG(K > 0 && N_total > 0 && (K % kGroup) == 0);
+    awq_unpack_kernel<<<dim3((K / 8 + 127) / 128, N_total), 128, 0, (cudaStream_t)stream>>>(
+        (const unsigned char*)packed, K, N_total, (__half*)out);
+    count_launches(1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
+
+extern "C" int umb_awq_gemm_f16(const void* x, int64_t ldx, const void* packed, void* y, int64_t ldy, int M, int K,
+                                int N_total, int group, const umb_epilogue_t* epilogue, void* workspace,
+                                size_t workspace_bytes, umb_stream_t stream) {
+    if (group != kGroup) return UMB_ERR_UNSUPPORTED;
+    return gemm_common(true, x, ldx, packed, 0, y, ldy, M, K, N_total, epilogue, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int umb_gemm_f16(const void* x, int64_t ldx, const void* w, int64_t ldw, void* y, int64_t ldy, int M, int K,
+                            int N, const umb_epilogue_t* epilogue, void* workspace, size_t workspace_bytes,
+                            umb_stream_t stream) {
+    return gemm_common(false, x, ldx, w, ldw, y, ldy, M, K, N, epilogue, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int umb_probe_umma(const void* a, const void* b, float* d, int mode, umb_stream_t stream) {
+    UMB_CHECK_ARG(a && b && d && (mode == 0 || mode == 1));
+    probe_umma_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, d, mode);
+    count_launches(1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
+
+extern "C" int umb_awq_gemm_f16_simt(const void* x, int64_t ldx, const void* packed, void* y, int64_t ldy, int M, int K,
+                                     int N_total, umb_stream_t stream) {
+    UMB_CHECK_ARG(x && packed && y && M >= 1 && K > 0 && (K % kGroup) == 0 && N_total > 0);
+    awq_gemm_simt_kernel<<<(N_total + kTileN - 1) / kTileN, 128, 0, (cudaStream_t)stream>>>(
+        (const unsigned char*)packed, (const __half*)x, ldx, (__half*)y, ldy, M, K, N_total);
+    count_launches(1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
