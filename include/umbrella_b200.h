@@ -106,7 +106,9 @@ int umb_gemm_f16(const void* x, int64_t ldx, const void* w, int64_t ldw, void* y
  * ---------------------------------------------------------------------------------------------- */
 enum {
     UMB_MASK_TREE = 0,   /* row i sees [0, prefix_len) and prefix_len + j for every set bit j of
-                            tree_bits[i, :] (u32 words, bit j%32 of word j/32)                    */
+                            tree_bits[i, :] (u32 words, bit j%32 of word j/32), j < kv_len - prefix_len.
+                            The rows may be a slice of the tree (one level of the draft's build_tree):
+                            pass tree_bits + first_row * tree_words                               */
     UMB_MASK_DENSE = 1,  /* row i sees j iff dense_mask[i * mask_stride + j] != 0  (bool / u8)     */
     UMB_MASK_CAUSAL = 2  /* row i sees j <= prefix_len + i   (prefill / append)                    */
 };

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParam
         const int last_row = min(rows_total, (int)(blockIdx.x + 1) * kBM) - 1;
         kv_hi = min(kv_hi, prefix_len + last_row / p.G + 1);
     } else if (p.mask_mode == UMB_MASK_TREE) {
-        kv_hi = min(kv_hi, prefix_len + p.qo);
+        kv_hi = min(kv_hi, prefix_len + p.tree_words * 32);   // columns the bitmask can describe
     }
     const int n_tiles = (kv_hi + kBN - 1) / kBN;
     const int tiles_per_split = (n_tiles + p.splits - 1) / p.splits;
@@ -358,7 +358,7 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
     UMB_CHECK_ARG((kv_tok_stride % 8) == 0 && (kv_head_stride % 8) == 0);
     UMB_CHECK_ARG((((uintptr_t)q | (uintptr_t)k_cache | (uintptr_t)v_cache | (uintptr_t)out) & 15) == 0);
     if (head_dim != 64 && head_dim != 128) return UMB_ERR_UNSUPPORTED;
-    if (mask->mask_mode == UMB_MASK_TREE) UMB_CHECK_ARG(mask->tree_bits && mask->tree_words * 32 >= qo);
+    if (mask->mask_mode == UMB_MASK_TREE) UMB_CHECK_ARG(mask->tree_bits && mask->tree_words >= 1);
     if (mask->mask_mode == UMB_MASK_DENSE) UMB_CHECK_ARG(mask->dense_mask && mask->mask_stride >= kv_len);
     UMB_CHECK_ARG(mask->mask_mode >= 0 && mask->mask_mode <= 2);
 

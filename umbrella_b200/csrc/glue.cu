@@ -73,7 +73,7 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gate, const __half* _
     for (int j = 0; j < 8; ++j) {
         const float f = __half2float(g.h[j]);
         const __half s = __float2half_rn(f / (1.f + expf(-f)));   // F.silu on an fp16 tensor: fp32 maths, one rounding
-        o.h[j] = __hmul(s, u.h[j]);                               // fp16 * fp16 tensor product
+        o.h[j] = __hmul_rn(s, u.h[j]);                            // fp16 * fp16 tensor product
     }
     reinterpret_cast<uint4*>(y)[v] = o.u;
 }
@@ -124,8 +124,10 @@ __global__ void rope_append_kernel(const __half* __restrict__ qkv, int64_t ld_qk
     const __half s0 = sin_t[pos * D + d], s1 = sin_t[pos * D + d + half_d];
     const __half x0 = src[d], x1 = src[d + half_d];
     // (x * cos) + (rotate_half(x) * sin), rotate_half = cat(-x[D/2:], x[:D/2])
-    const __half o0 = __hadd(__hmul(x0, c0), __hmul(__hneg(x1), s0));
-    const __half o1 = __hadd(__hmul(x1, c1), __hmul(x0, s1));
+    // _rn forms: each product and the sum round separately (no contraction into an fma), as the
+    // reference's three fp16 tensor ops do
+    const __half o0 = __hadd_rn(__hmul_rn(x0, c0), __hmul_rn(__hneg(x1), s0));
+    const __half o1 = __hadd_rn(__hmul_rn(x1, c1), __hmul_rn(x0, s1));
     __half* dst = h < Hq ? q_out + ((int64_t)t * Hq + h) * D
                          : k_cache + (int64_t)(kv_offset + t) * kv_tok_stride + (int64_t)(h - Hq) * kv_head_stride;
     dst[d] = o0;

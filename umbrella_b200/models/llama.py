@@ -113,7 +113,7 @@ class Llama:
         self.num_key_value_heads = shape.num_key_value_heads
         self.num_key_value_groups = self.num_heads // self.num_key_value_heads
         self.num_layers = shape.num_hidden_layers if num_layers is None else num_layers
-        self.eos_tokens = list(shape.eos_token_id)
+        self.eos_tokens = list(getattr(shape, "eos_token_id", (128001, 128008, 128009)))
         self.norm_variance_epsilon = shape.rms_norm_eps
         self._c_model = None
         self.layer_weights: list[dict] = []

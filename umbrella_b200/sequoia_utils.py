@@ -1,0 +1,116 @@
+"""Sequoia growmaps: schema, loader, builders (reference umbrella/sequoia_utils.py:40-130 and the
+tree set-up of static_speculation_engine.py:49-86).
+
+Growmap JSON schema (kept byte-compatible): ``{roots, branches, Successors, mask, depth, size}``.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+DEFAULT_ACC = [0.65, 0.2, 0.1, 0.05]          # sequoia_utils.py:7
+TREES_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "trees")
+
+
+def successor_list_to_mask(successors: list[list[int]]) -> list[list[int]]:
+    """mask[i][j] = 1 iff j is i or an ancestor of i (sequoia_utils.py:40-79)."""
+    n = len(successors)
+    parent = [-1] * n
+    for v, succ in enumerate(successors):
+        for c in succ:
+            parent[c] = v
+    mask = [[0] * n for _ in range(n)]
+    for i in range(n):
+        j = i
+        while j >= 0:
+            mask[i][j] = 1
+            j = parent[j]
+    return mask
+
+
+def growmap_from_successors(successors: list[list[int]]) -> dict:
+    n = len(successors)
+    depth = [0] * n
+    for v in range(n):
+        for c in successors[v]:
+            if c <= v:
+                raise ValueError("growmaps are stored in level order (parent < child)")
+            depth[c] = depth[v] + 1
+    levels = max(depth) + 1
+    roots = [[v for v in range(n) if depth[v] == d] for d in range(levels)]
+    branches = [[len(successors[v]) for v in level] for level in roots]
+    return {"roots": roots, "branches": branches, "Successors": [list(s) for s in successors],
+            "mask": successor_list_to_mask(successors), "depth": depth, "size": n}
+
+
+def generate_sequoia_tree(width: int, depth: int, acc: list[float] | None = None, json_file: str | None = None) -> dict:
+    """Greedy tree constructor with the reference's semantics (sequoia_utils.py:83-130): per level,
+    the ``width`` best (parent, rank) candidates by accumulated log-acceptance (float32, torch.topk
+    tie order), children attached to the *sorted* parent list."""
+    if acc is None:
+        assert width <= 4, "Using default acceptance rate vector, require width<=4"
+        acc = DEFAULT_ACC
+    log_acc = torch.log(torch.tensor(acc, dtype=torch.float32))
+    beams = len(acc)
+    successors: list[list[int]] = [[]]
+    level_scores = torch.zeros(1)
+    level_start = 0
+    for lvl in range(depth):
+        cand = log_acc.repeat(level_scores.numel()) + level_scores.repeat_interleave(beams)
+        best, idx = cand.topk(k=width)
+        parents = sorted((idx // beams + level_start).tolist())
+        first_child = len(successors)
+        successors.extend([[] for _ in range(width)])
+        for j, p in enumerate(parents):
+            successors[p].append(first_child + j)
+        level_scores = best
+        level_start = first_child
+    gm = growmap_from_successors(successors)
+    if json_file is not None:
+        with open(json_file, "w") as f:
+            json.dump(gm, f)
+    return gm
+
+
+def load_growmap(path: str) -> dict:
+    """Load a growmap; bare file names resolve against the packaged trees directory, and a path into
+    the reference checkout (``../umbrella/trees/x.json``) resolves to the same file name."""
+    if not os.path.exists(path):
+        alt = os.path.join(TREES_DIR, os.path.basename(path))
+        if os.path.exists(alt):
+            path = alt
+    with open(path) as f:
+        gm = json.load(f)
+    if "Successors" not in gm or "size" not in gm:
+        raise ValueError(f"{path}: not a growmap")
+    if "mask" not in gm or "depth" not in gm or "roots" not in gm or "branches" not in gm:
+        gm = growmap_from_successors(gm["Successors"])
+    return gm
+
+
+def tree_bits_from_mask(mask) -> np.ndarray:
+    """bool [N, N] ancestor-or-self mask -> int32 words [N, ceil(N/32)], bit j%32 of word j//32."""
+    m = np.asarray(mask).astype(bool)
+    n = m.shape[0]
+    words = (m.shape[1] + 31) // 32
+    padded = np.zeros((n, words * 32), dtype=np.uint64)
+    padded[:, :m.shape[1]] = m
+    weights = (np.uint64(1) << np.arange(32, dtype=np.uint64))
+    out = (padded.reshape(n, words, 32) * weights).sum(axis=-1).astype(np.uint32)
+    return out.view(np.int32)
+
+
+def expected_accept_length(gm: dict, acc: list[float] | None = None) -> float:
+    """E[tokens per verify] when the rank-r child of any node is accepted with probability acc[r]
+    (sum over nodes of the product of edge probabilities) -- the figure a scripted run converges to."""
+    acc = DEFAULT_ACC if acc is None else acc
+    succ = gm["Successors"]
+    prob = [0.0] * gm["size"]
+    prob[0] = 1.0
+    for v in range(gm["size"]):
+        for r, c in enumerate(succ[v]):
+            prob[c] = prob[v] * (acc[r] if r < len(acc) else 0.0)
+    return float(sum(prob))
