@@ -127,7 +127,9 @@ size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int head_dim, int 
 
 /* q fp16 [qo, Hq, D]; k/v: base of this layer's cache, token stride / head stride in elements
  * ([S,Hkv,D]: tok = Hkv*D, head = D;  [Hkv,S,D]: tok = D, head = S*D); out fp16 [qo, Hq, D].
- * kv_len = number of valid cache rows (after the append).  sm_scale <= 0 -> 1/sqrt(D). */
+ * kv_len = number of valid cache rows (after the append).  sm_scale <= 0 -> 1/sqrt(D).
+ * `workspace` (umb_tree_attn_workspace_bytes) holds the split-KV partials; without it the KV range
+ * is not split across CTAs. */
 int umb_tree_attn_f16(const void* q, const void* k_cache, const void* v_cache, void* out, int qo, int kv_len,
                       int num_q_heads, int num_kv_heads, int head_dim, int64_t kv_tok_stride, int64_t kv_head_stride,
                       const umb_attn_mask_t* mask, float sm_scale, float soft_cap, void* workspace,

@@ -37,6 +37,7 @@ struct AttnParams {
     int splits;
     float* part_o;      // [splits][Hkv * qo * G][D]
     float2* part_ml;    // [splits][Hkv * qo * G]  (running max in the log2 domain, running sum)
+    int* counters;      // [Hkv * row_tiles] arrival counters of the split CTAs (zero between launches)
 };
 
 constexpr int kAttnThreads = 128;
@@ -89,7 +90,41 @@ __device__ __forceinline__ void load_tile(__half* smem, const __half* gbase, int
     }
 }
 
-template <int D>
+// 64-column visibility window of one query row for the kv tile starting at col0 (bit i = column col0 + i).
+// Built once per (row, tile) -- the per-element work is then a constant-position bit test.
+__device__ __forceinline__ unsigned long long row_window(const AttnParams& p, int tok, bool row_ok, int col0, int kv_hi,
+                                                         int prefix_len) {
+    if (!row_ok) return 0ull;
+    const int n_valid = min(kBN, kv_hi - col0);                        // columns of this tile that exist
+    const unsigned long long exist = n_valid >= 64 ? ~0ull : ((1ull << n_valid) - 1ull);
+    unsigned long long allow;
+    if (p.mask_mode == UMB_MASK_CAUSAL) {
+        const int n = prefix_len + tok + 1 - col0;                     // columns j <= prefix_len + tok
+        allow = n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull));
+    } else if (p.mask_mode == UMB_MASK_TREE) {
+        const int np = prefix_len - col0;                              // leading prefix columns: always visible
+        allow = np >= 64 ? ~0ull : (np <= 0 ? 0ull : ((1ull << np) - 1ull));
+        if (np < 64) {
+            const uint32_t* bits = p.tree_bits + (int64_t)tok * p.tree_words;
+            const int start = -np;                                     // tree bit index of column col0 (may be < 0)
+#pragma unroll 1
+            for (int w = 0; w < p.tree_words; ++w) {                   // place tree word w at columns [32w - start, +32)
+                const int pos = 32 * w - start;
+                if (pos <= -32 || pos >= 64) continue;
+                const unsigned long long v = bits[w];
+                allow |= pos >= 0 ? (v << pos) : (v >> (-pos));
+            }
+        }
+    } else {
+        allow = 0ull;
+        const uint8_t* mrow = p.dense_mask + (int64_t)tok * p.mask_stride + col0;
+#pragma unroll 1
+        for (int i = 0; i < n_valid; ++i) allow |= (unsigned long long)(mrow[i] != 0) << i;
+    }
+    return allow & exist;
+}
+
+template <int D, bool kSoftCap>
 __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [2][kBN][D]
@@ -188,43 +223,33 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParam
             }
         }
 
-        // ---- scale, soft-cap, mask ----
+        // ---- soft-cap (Gemma only), mask ----
         const int col0 = tile * kBN;
+        if constexpr (kSoftCap) {
+#pragma unroll
+            for (int nb = 0; nb < kBN / 8; ++nb)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    s[nb][e] = p.soft_cap * tanhf(s[nb][e] * p.sm_scale / p.soft_cap) / p.sm_scale;   // back in raw units
+        }
         const bool need_mask = (col0 + kBN > kv_hi) || (p.mask_mode == UMB_MASK_DENSE) || (col0 + kBN > prefix_len);
+        if (need_mask) {
 #pragma unroll
-        for (int nb = 0; nb < kBN / 8; ++nb) {
+            for (int ri = 0; ri < 2; ++ri) {
+                const unsigned long long win = row_window(p, tok[ri], row_ok[ri], col0, kv_hi, prefix_len) >> (t4 * 2);
+                const uint32_t lo = (uint32_t)win, hi = (uint32_t)(win >> 32);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float x = s[nb][e];
-                if (p.soft_cap > 0.f) {
-                    x = p.soft_cap * tanhf(x * p.sm_scale / p.soft_cap) * 1.4426950408889634f;
-                } else {
-                    x *= p.scale_log2;
+                for (int nb = 0; nb < kBN / 8; ++nb) {
+                    const uint32_t wbits = nb < 4 ? lo : hi;
+                    const int b = (nb & 3) * 8;
+                    if (!((wbits >> b) & 1u)) s[nb][2 * ri] = -INFINITY;
+                    if (!((wbits >> (b + 1)) & 1u)) s[nb][2 * ri + 1] = -INFINITY;
                 }
-                if (need_mask) {
-                    const int ri = e >> 1;
-                    const int j = col0 + nb * 8 + t4 * 2 + (e & 1);
-                    bool ok = row_ok[ri] && j < kv_hi;
-                    if (ok) {
-                        if (p.mask_mode == UMB_MASK_TREE) {
-                            if (j >= prefix_len) {
-                                const int b = j - prefix_len;
-                                ok = (p.tree_bits[(int64_t)tok[ri] * p.tree_words + (b >> 5)] >> (b & 31)) & 1u;
-                            }
-                        } else if (p.mask_mode == UMB_MASK_CAUSAL) {
-                            ok = j <= prefix_len + tok[ri];
-                        } else {
-                            ok = p.dense_mask[(int64_t)tok[ri] * p.mask_stride + j] != 0;
-                        }
-                    }
-                    if (!ok) x = -INFINITY;
-                }
-                s[nb][e] = x;
             }
         }
 
-        // ---- online softmax (rows g4 and g4 + 8) ----
-        float m_new[2], corr[2];
+        // ---- online softmax (rows g4 and g4 + 8), scores still unscaled: exp2((s - m) * scale_log2) ----
+        float corr[2];
 #pragma unroll
         for (int ri = 0; ri < 2; ++ri) {
             float mx = -INFINITY;
@@ -232,13 +257,14 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParam
             for (int nb = 0; nb < kBN / 8; ++nb) mx = fmaxf(mx, fmaxf(s[nb][2 * ri], s[nb][2 * ri + 1]));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            m_new[ri] = fmaxf(m_run[ri], mx);
-            const float m_use = m_new[ri] == -INFINITY ? 0.f : m_new[ri];
-            corr[ri] = exp2f(m_run[ri] - m_use);                    // m_run = -inf -> 0
+            const float m_new = fmaxf(m_run[ri], mx * p.scale_log2);       // running max lives in the log2 domain
+            const float m_use = m_new == -INFINITY ? 0.f : m_new;
+            corr[ri] = exp2f(m_run[ri] - m_use);                            // m_run = -inf -> 0
             float sum = 0.f;
 #pragma unroll
             for (int nb = 0; nb < kBN / 8; ++nb) {
-                const float p0 = exp2f(s[nb][2 * ri] - m_use), p1 = exp2f(s[nb][2 * ri + 1] - m_use);
+                const float p0 = exp2f(fmaf(s[nb][2 * ri], p.scale_log2, -m_use));
+                const float p1 = exp2f(fmaf(s[nb][2 * ri + 1], p.scale_log2, -m_use));
                 s[nb][2 * ri] = p0;
                 s[nb][2 * ri + 1] = p1;
                 sum += p0 + p1;
@@ -246,7 +272,7 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParam
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
             l_run[ri] = l_run[ri] * corr[ri] + sum;
-            m_run[ri] = m_new[ri];
+            m_run[ri] = m_new;
         }
 #pragma unroll
         for (int i = 0; i < D / 8; ++i) {
@@ -304,18 +330,300 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Latency-oriented variant for small query counts (tree verify, draft levels, short prefill
+// chunks): one CTA per (16-row slab, kv head[, kv split]); its four warps take kv tiles of 32 rows
+// round-robin, each with a private double-buffered K/V ring in shared memory (no CTA-wide barrier
+// in the loop), and merge their (m, l, o) partials through shared memory at the end.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSBN = 32;
+
+template <int D>
+__device__ __forceinline__ void load_tile_warp(__half* smem, const __half* gbase, int64_t tok_stride, int row0, int kv_hi,
+                                               int lane) {
+    constexpr int kChunks = D / 8;
+#pragma unroll
+    for (int i = lane; i < kSBN * kChunks; i += 32) {
+        const int r = i / kChunks, c = i % kChunks;
+        const int row = row0 + r;
+        const bool ok = row < kv_hi;
+        cp_async16(tile_ptr<D>(smem, r, c), gbase + (int64_t)(ok ? row : 0) * tok_stride + c * 8, ok);
+    }
+}
+
+// 32-column visibility window (bit i = column col0 + i)
+__device__ __forceinline__ uint32_t row_window32(const AttnParams& p, int tok, bool row_ok, int col0, int kv_hi,
+                                                 int prefix_len) {
+    if (!row_ok) return 0u;
+    const int n_valid = min(kSBN, kv_hi - col0);
+    const uint32_t exist = n_valid >= 32 ? ~0u : ((1u << n_valid) - 1u);
+    uint32_t allow;
+    if (p.mask_mode == UMB_MASK_CAUSAL) {
+        const int n = prefix_len + tok + 1 - col0;
+        allow = n >= 32 ? ~0u : (n <= 0 ? 0u : ((1u << n) - 1u));
+    } else if (p.mask_mode == UMB_MASK_TREE) {
+        const int np = prefix_len - col0;
+        allow = np >= 32 ? ~0u : (np <= 0 ? 0u : ((1u << np) - 1u));
+        if (np < 32) {
+            const uint32_t* bits = p.tree_bits + (int64_t)tok * p.tree_words;
+            const int start = -np;                                   // tree bit index of column col0
+            const int w0 = start >> 5;                               // floor division (start may be negative)
+            const int sh = start & 31;
+            const uint32_t lo = (w0 >= 0 && w0 < p.tree_words) ? bits[w0] : 0u;
+            const uint32_t hi = (w0 + 1 >= 0 && w0 + 1 < p.tree_words) ? bits[w0 + 1] : 0u;
+            allow |= sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+        }
+    } else {
+        allow = 0u;
+        const uint8_t* mrow = p.dense_mask + (int64_t)tok * p.mask_stride + col0;
+#pragma unroll 1
+        for (int i = 0; i < n_valid; ++i) allow |= (uint32_t)(mrow[i] != 0) << i;
+    }
+    return allow & exist;
+}
+
+template <int D, bool kSoftCap>
+__global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const AttnParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    const int hkv = blockIdx.y, split = blockIdx.z;
+    const int rows_total = p.qo * p.G;
+    const int prefix_len = p.dyn ? p.dyn[0] : p.prefix_len;
+    const int kv_len = p.dyn ? p.dyn[1] : p.kv_len;
+    // per-warp ring: [2 stages][K | V][kSBN][D]
+    __half* ring = reinterpret_cast<__half*>(smem_raw) + warp * (4 * kSBN * D);
+
+    const int row_base = blockIdx.x * 16;
+    int row[2], tok[2];
+    bool row_ok[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        row[i] = row_base + g4 + 8 * i;
+        row_ok[i] = row[i] < rows_total;
+        tok[i] = row_ok[i] ? row[i] / p.G : 0;
+    }
+    uint32_t qf[D / 16][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int hq = hkv * p.G + (row_ok[i] ? row[i] % p.G : 0);
+        const __half* qr = p.q + ((int64_t)tok[i] * p.Hq + hq) * D;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+            uint32_t lo = 0, hi = 0;
+            if (row_ok[i]) {
+                lo = *reinterpret_cast<const uint32_t*>(qr + ks * 16 + t4 * 2);
+                hi = *reinterpret_cast<const uint32_t*>(qr + ks * 16 + 8 + t4 * 2);
+            }
+            qf[ks][i] = lo;
+            qf[ks][2 + i] = hi;
+        }
+    }
+
+    int kv_hi = kv_len;
+    if (p.mask_mode == UMB_MASK_CAUSAL) {
+        const int last_row = min(rows_total, row_base + 16) - 1;
+        kv_hi = min(kv_hi, prefix_len + last_row / p.G + 1);
+    } else if (p.mask_mode == UMB_MASK_TREE) {
+        kv_hi = min(kv_hi, prefix_len + p.tree_words * 32);
+    }
+    const int n_tiles = (kv_hi + kSBN - 1) / kSBN;
+    const int tiles_per_split = (n_tiles + p.splits - 1) / p.splits;
+    const int tile_lo = split * tiles_per_split;
+    const int tile_hi = min(n_tiles, tile_lo + tiles_per_split);
+    const __half* kg = p.k + (int64_t)hkv * p.kv_head_stride;
+    const __half* vg = p.v + (int64_t)hkv * p.kv_head_stride;
+
+    float o_acc[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+    int tile = tile_lo + warp;
+    if (tile < tile_hi) {
+        load_tile_warp<D>(ring, kg, p.kv_tok_stride, tile * kSBN, kv_hi, lane);
+        load_tile_warp<D>(ring + kSBN * D, vg, p.kv_tok_stride, tile * kSBN, kv_hi, lane);
+        cp_async_commit();
+    }
+    for (int it = 0; tile < tile_hi; tile += 4, ++it) {
+        const int buf = it & 1;
+        if (tile + 4 < tile_hi) {
+            __half* nxt = ring + (buf ^ 1) * (2 * kSBN * D);
+            load_tile_warp<D>(nxt, kg, p.kv_tok_stride, (tile + 4) * kSBN, kv_hi, lane);
+            load_tile_warp<D>(nxt + kSBN * D, vg, p.kv_tok_stride, (tile + 4) * kSBN, kv_hi, lane);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        __half* tK = ring + buf * (2 * kSBN * D);
+        __half* tV = tK + kSBN * D;
+
+        float s[kSBN / 8][4];
+#pragma unroll
+        for (int i = 0; i < kSBN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+#pragma unroll
+            for (int nb = 0; nb < kSBN / 8; nb += 2) {
+                uint32_t b[4];
+                const int r = nb * 8 + (lane & 7) + ((lane >> 4) << 3);
+                const int c = ks * 2 + ((lane >> 3) & 1);
+                ldmatrix_x4(b, tile_ptr<D>(tK, r, c));
+                mma_16816(s[nb], qf[ks], b[0], b[1]);
+                mma_16816(s[nb + 1], qf[ks], b[2], b[3]);
+            }
+        }
+        const int col0 = tile * kSBN;
+        if constexpr (kSoftCap) {
+#pragma unroll
+            for (int nb = 0; nb < kSBN / 8; ++nb)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    s[nb][e] = p.soft_cap * tanhf(s[nb][e] * p.sm_scale / p.soft_cap) / p.sm_scale;
+        }
+        const bool need_mask = (col0 + kSBN > kv_hi) || (p.mask_mode == UMB_MASK_DENSE) || (col0 + kSBN > prefix_len);
+        if (need_mask) {
+#pragma unroll
+            for (int ri = 0; ri < 2; ++ri) {
+                const uint32_t win = row_window32(p, tok[ri], row_ok[ri], col0, kv_hi, prefix_len) >> (t4 * 2);
+#pragma unroll
+                for (int nb = 0; nb < kSBN / 8; ++nb) {
+                    if (!((win >> (nb * 8)) & 1u)) s[nb][2 * ri] = -INFINITY;
+                    if (!((win >> (nb * 8 + 1)) & 1u)) s[nb][2 * ri + 1] = -INFINITY;
+                }
+            }
+        }
+        float corr[2];
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nb = 0; nb < kSBN / 8; ++nb) mx = fmaxf(mx, fmaxf(s[nb][2 * ri], s[nb][2 * ri + 1]));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float m_new = fmaxf(m_run[ri], mx * p.scale_log2);
+            const float m_use = m_new == -INFINITY ? 0.f : m_new;
+            corr[ri] = exp2f(m_run[ri] - m_use);
+            float sum = 0.f;
+#pragma unroll
+            for (int nb = 0; nb < kSBN / 8; ++nb) {
+                const float p0 = exp2f(fmaf(s[nb][2 * ri], p.scale_log2, -m_use));
+                const float p1 = exp2f(fmaf(s[nb][2 * ri + 1], p.scale_log2, -m_use));
+                s[nb][2 * ri] = p0;
+                s[nb][2 * ri + 1] = p1;
+                sum += p0 + p1;
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            l_run[ri] = l_run[ri] * corr[ri] + sum;
+            m_run[ri] = m_new;
+        }
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+            o_acc[i][0] *= corr[0];
+            o_acc[i][1] *= corr[0];
+            o_acc[i][2] *= corr[1];
+            o_acc[i][3] *= corr[1];
+        }
+#pragma unroll
+        for (int ks = 0; ks < kSBN / 16; ++ks) {
+            uint32_t a[4];
+            a[0] = pack_half2(s[2 * ks][0], s[2 * ks][1]);
+            a[1] = pack_half2(s[2 * ks][2], s[2 * ks][3]);
+            a[2] = pack_half2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+            a[3] = pack_half2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+            for (int db = 0; db < D / 8; db += 2) {
+                uint32_t b[4];
+                const int r = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+                const int c = db + (lane >> 4);
+                ldmatrix_x4_trans(b, tile_ptr<D>(tV, r, c));
+                mma_16816(o_acc[db], a, b[0], b[1]);
+                mma_16816(o_acc[db + 1], a, b[2], b[3]);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- merge the four warps' partials through shared memory ----
+    __syncthreads();                                   // every warp is done with its ring
+    constexpr int kLd = D + 4;                         // padded fp32 row
+    float* s_o = reinterpret_cast<float*>(smem_raw);   // [4][16][kLd]
+    float* s_m = s_o + 4 * 16 * kLd;                   // [4][16]
+    float* s_l = s_m + 64;                             // [4][16]
+#pragma unroll
+    for (int ri = 0; ri < 2; ++ri) {
+        const int r = g4 + 8 * ri;
+        float* orow = s_o + (warp * 16 + r) * kLd;
+#pragma unroll
+        for (int db = 0; db < D / 8; ++db)
+            *reinterpret_cast<float2*>(orow + db * 8 + t4 * 2) = make_float2(o_acc[db][2 * ri], o_acc[db][2 * ri + 1]);
+        if (t4 == 0) {
+            s_m[warp * 16 + r] = m_run[ri];
+            s_l[warp * 16 + r] = l_run[ri];
+        }
+    }
+    __syncthreads();
+    {
+        const int r = threadIdx.x >> 3;                // 16 rows x 8 threads
+        const int c0 = (threadIdx.x & 7) * (D / 8);    // D/8 consecutive columns per thread
+        const int grow_in_head = row_base + r;
+        if (grow_in_head < rows_total) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) m = fmaxf(m, s_m[w * 16 + r]);
+            const float m_use = m == -INFINITY ? 0.f : m;
+            float wgt[4], l = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                wgt[w] = exp2f(s_m[w * 16 + r] - m_use);
+                l += s_l[w * 16 + r] * wgt[w];
+            }
+            const int tk = grow_in_head / p.G, hq = hkv * p.G + grow_in_head % p.G;
+            if (p.splits == 1) {
+                const float inv = l > 0.f ? 1.f / l : 0.f;
+                __half* orow = p.out + ((int64_t)tk * p.Hq + hq) * D + c0;
+#pragma unroll
+                for (int c = 0; c < D / 8; c += 2) {
+                    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        v0 += s_o[(w * 16 + r) * kLd + c0 + c] * wgt[w];
+                        v1 += s_o[(w * 16 + r) * kLd + c0 + c + 1] * wgt[w];
+                    }
+                    *reinterpret_cast<uint32_t*>(orow + c) = pack_half2(v0 * inv, v1 * inv);
+                }
+            } else {
+                const int64_t grow = (int64_t)split * p.Hkv * rows_total + (int64_t)hkv * rows_total + grow_in_head;
+                float* orow = p.part_o + grow * D + c0;
+#pragma unroll
+                for (int c = 0; c < D / 8; ++c) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) v += s_o[(w * 16 + r) * kLd + c0 + c] * wgt[w];
+                    orow[c] = v;
+                }
+                if ((threadIdx.x & 7) == 0) p.part_ml[grow] = make_float2(m, l);
+            }
+        }
+    }
+}
+
 // grid (Hkv * qo * G); block D threads.  Merges the per-split (m, l, o) triples.
 template <int D>
 __global__ void __launch_bounds__(D) tree_attn_combine_kernel(const AttnParams p) {
     const int rows_total = p.qo * p.G;
     const int grow = blockIdx.x;                 // hkv * rows_total + row
     const int hkv = grow / rows_total, row = grow % rows_total;
+    const int64_t stride = (int64_t)p.Hkv * rows_total;
     float m = -INFINITY;
-    for (int s = 0; s < p.splits; ++s) m = fmaxf(m, p.part_ml[(int64_t)s * p.Hkv * rows_total + grow].x);
+    for (int s = 0; s < p.splits; ++s) m = fmaxf(m, p.part_ml[s * stride + grow].x);
     const float m_use = m == -INFINITY ? 0.f : m;
     float l = 0.f, o = 0.f;
     for (int s = 0; s < p.splits; ++s) {
-        const int64_t idx = (int64_t)s * p.Hkv * rows_total + grow;
+        const int64_t idx = s * stride + grow;
         const float2 ml = p.part_ml[idx];
         const float w = exp2f(ml.x - m_use);
         l += ml.y * w;
@@ -323,18 +631,6 @@ __global__ void __launch_bounds__(D) tree_attn_combine_kernel(const AttnParams p
     }
     const int tok = row / p.G, hq = hkv * p.G + row % p.G;
     p.out[((int64_t)tok * p.Hq + hq) * D + threadIdx.x] = __float2half_rn(l > 0.f ? o / l : 0.f);
-}
-
-static int choose_splits(int qo, int G, int Hkv, int kv_len) {
-    const int row_tiles = (qo * G + kBM - 1) / kBM;
-    const int kv_tiles = (kv_len + kBN - 1) / kBN;
-    const int base = row_tiles * Hkv;
-    int splits = (2 * sm_count() + base - 1) / base;      // aim at ~2 CTAs per SM
-    splits = splits < 1 ? 1 : splits;
-    const int max_by_len = (kv_tiles + 1) / 2;              // at least two kv tiles per split
-    splits = splits > max_by_len ? max_by_len : splits;
-    splits = splits > 64 ? 64 : splits;
-    return splits < 1 ? 1 : splits;
 }
 
 }  // namespace umb
@@ -345,7 +641,36 @@ extern "C" size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int hea
     (void)max_kv_len;
     if (qo < 1 || num_q_heads < 1 || head_dim < 1) return 0;
     const size_t rows = (size_t)qo * num_q_heads;
-    return 64 * rows * ((size_t)head_dim * sizeof(float) + sizeof(float2)) + 256;
+    return 32 * rows * ((size_t)head_dim * sizeof(float) + sizeof(float2)) + 256;
+}
+
+template <int D, bool kSoftCap>
+static int launch_attn(const AttnParams& p, bool slab, dim3 grid, cudaStream_t st) {
+    if (slab) {
+        const size_t smem = (size_t)4 * 4 * kSBN * D * sizeof(__half);          // 4 warps x 2 stages x (K|V)
+        static bool attr_done = false;
+        if (!attr_done && smem > 48 * 1024) {
+            UMB_CUDA(cudaFuncSetAttribute(tree_attn_slab_kernel<D, kSoftCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        tree_attn_slab_kernel<D, kSoftCap><<<grid, kAttnThreads, smem, st>>>(p);
+    } else {
+        const size_t smem = (size_t)4 * kBN * D * sizeof(__half);
+        static bool attr_done = false;
+        if (!attr_done && smem > 48 * 1024) {
+            UMB_CUDA(cudaFuncSetAttribute(tree_attn_kernel<D, kSoftCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        tree_attn_kernel<D, kSoftCap><<<grid, kAttnThreads, smem, st>>>(p);
+    }
+    int launches = 1;
+    if (p.splits > 1) {
+        tree_attn_combine_kernel<D><<<(unsigned)(p.Hkv * p.qo * p.G), D, 0, st>>>(p);
+        launches = 2;
+    }
+    count_launches(launches);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
 }
 
 extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void* v_cache, void* out, int qo, int kv_len,
@@ -358,9 +683,9 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
     UMB_CHECK_ARG((kv_tok_stride % 8) == 0 && (kv_head_stride % 8) == 0);
     UMB_CHECK_ARG((((uintptr_t)q | (uintptr_t)k_cache | (uintptr_t)v_cache | (uintptr_t)out) & 15) == 0);
     if (head_dim != 64 && head_dim != 128) return UMB_ERR_UNSUPPORTED;
+    UMB_CHECK_ARG(mask->mask_mode >= 0 && mask->mask_mode <= 2);
     if (mask->mask_mode == UMB_MASK_TREE) UMB_CHECK_ARG(mask->tree_bits && mask->tree_words >= 1);
     if (mask->mask_mode == UMB_MASK_DENSE) UMB_CHECK_ARG(mask->dense_mask && mask->mask_stride >= kv_len);
-    UMB_CHECK_ARG(mask->mask_mode >= 0 && mask->mask_mode <= 2);
 
     AttnParams p{};
     p.q = (const __half*)q;
@@ -384,38 +709,35 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
     p.sm_scale = sm_scale > 0.f ? sm_scale : 1.0f / sqrtf((float)head_dim);
     p.scale_log2 = p.sm_scale * 1.4426950408889634f;
     p.soft_cap = soft_cap;
-    p.splits = choose_splits(qo, p.G, p.Hkv, kv_len);
+
+    // kernel + split selection.  slab kernel: K/V is re-read once per 16-row slab (L2), so it is used
+    // while that re-read is cheap; long contexts with many slabs go to the 64-row tile kernel.
+    const int rows_total = qo * p.G;
+    const int slabs = (rows_total + 15) / 16;
+    const bool slab = !(kv_len > 8192 && slabs > 2);
+    const int ctas_base = (slab ? slabs : (rows_total + kBM - 1) / kBM) * p.Hkv;
+    const int kv_tiles = (kv_len + (slab ? kSBN : kBN) - 1) / (slab ? kSBN : kBN);
+    const int tiles_per_cta_min = slab ? 32 : 4;              // slab CTAs run 4 tiles at a time (one per warp)
+    int splits = (kv_tiles + tiles_per_cta_min - 1) / tiles_per_cta_min;
+    const int by_ctas = (2 * sm_count()) / (ctas_base > 0 ? ctas_base : 1);
+    splits = splits > by_ctas ? by_ctas : splits;
+    splits = splits > 32 ? 32 : splits;
+    splits = splits < 1 ? 1 : splits;
     const size_t rows = (size_t)qo * num_q_heads;
-    if (p.splits > 1) {
-        const size_t need = (size_t)p.splits * rows * ((size_t)head_dim * sizeof(float) + sizeof(float2)) + 256;
-        if (!workspace || workspace_bytes < need) {
-            // shrink to what fits (1 split needs no workspace)
-            size_t per = rows * ((size_t)head_dim * sizeof(float) + sizeof(float2));
-            int fit = workspace && workspace_bytes > 256 ? (int)((workspace_bytes - 256) / per) : 1;
-            p.splits = fit < 1 ? 1 : (fit < p.splits ? fit : p.splits);
-        }
+    const size_t per_split = rows * ((size_t)head_dim * sizeof(float) + sizeof(float2));
+    if (splits > 1) {
+        const size_t avail = (workspace && workspace_bytes > 256) ? (workspace_bytes - 256) / per_split : 0;
+        if ((size_t)splits > avail) splits = avail < 1 ? 1 : (int)avail;
     }
-    if (p.splits > 1) {
-        uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    p.splits = splits;
+    if (splits > 1) {
+        const uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
         p.part_o = reinterpret_cast<float*>(base);
-        p.part_ml = reinterpret_cast<float2*>(base + (size_t)p.splits * rows * head_dim * sizeof(float));
+        p.part_ml = reinterpret_cast<float2*>(base + (size_t)splits * rows * head_dim * sizeof(float));
     }
-    const dim3 grid((qo * p.G + kBM - 1) / kBM, p.Hkv, p.splits);
-    const size_t smem = (size_t)4 * kBN * head_dim * sizeof(__half);
+    const dim3 grid(slab ? slabs : (rows_total + kBM - 1) / kBM, p.Hkv, splits);
     cudaStream_t st = (cudaStream_t)stream;
-    if (head_dim == 128) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            UMB_CUDA(cudaFuncSetAttribute(tree_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
-        tree_attn_kernel<128><<<grid, kAttnThreads, smem, st>>>(p);
-        if (p.splits > 1) tree_attn_combine_kernel<128><<<(unsigned)rows, 128, 0, st>>>(p);
-    } else {
-        tree_attn_kernel<64><<<grid, kAttnThreads, smem, st>>>(p);
-        if (p.splits > 1) tree_attn_combine_kernel<64><<<(unsigned)rows, 64, 0, st>>>(p);
-    }
-    count_launches(p.splits > 1 ? 2 : 1);
-    UMB_LAUNCH_CHECK();
-    return UMB_OK;
+    if (head_dim == 128)
+        return soft_cap > 0.f ? launch_attn<128, true>(p, slab, grid, st) : launch_attn<128, false>(p, slab, grid, st);
+    return soft_cap > 0.f ? launch_attn<64, true>(p, slab, grid, st) : launch_attn<64, false>(p, slab, grid, st);
 }

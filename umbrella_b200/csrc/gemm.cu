@@ -13,10 +13,11 @@
 // AWQ mainloop (per 128-feature x 128-k "unit" = one 8512-byte record of the repacked stream):
 //   warp 0      TMA producer: cp.async.bulk of the packed record + cp.async.bulk.tensor (SW128)
 //               of the x slab [MPAD, 128 k] into a kStages-deep shared-memory ring
-//   warps 2..9  dequant: thread = one feature row x 64 k; lop3 nibble -> fp16 (1024+q), exact
-//               hsub2 of (1024+z), one hmul2 by the group scale == fp16((q - z) * s), the same
-//               rounding as the reference kernels; the fp16 row goes straight to TENSOR MEMORY
-//               with tcgen05.st (no shared-memory round trip, no swizzle arithmetic)
+//   warps 2..13 dequant, three groups of four warps taking units round-robin: thread = one feature
+//               row x 128 k; one lop3 per nibble pair -> fp16 (1024+q | 1024+16q), an exact
+//               hsub2 / hfma2 removes the bias and the zero point, one hmul2 by the group scale
+//               == fp16((q - z) * s), the same rounding as the reference kernels; the fp16 row
+//               goes straight to TENSOR MEMORY with tcgen05.st (no shared-memory round trip)
 //   warp 1      one thread issues tcgen05.mma kind::f16 with A from TMEM, B from shared memory
 //   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator, fuse bias / residual / SiLU*up / fp32
 //               logits, fp16 rounding placed where the reference has fp16 tensors
@@ -35,9 +36,11 @@ constexpr int kGroup = 128;              // AWQ group size == k per AWQ unit
 constexpr int kRecordBytes = 8512;       // 8192 nibble bytes + 256 scale bytes + 64 zero bytes
 constexpr int kRecScaleOff = 8192;
 constexpr int kRecZeroOff = 8448;
-constexpr int kGemmThreads = 320;        // 10 warps
+constexpr int kDqGroups = 3;              // dequant warp groups (4 warps each, one per TMEM lane quarter)
+constexpr int kGemmThreads = 64 + 128 * kDqGroups;   // producer + MMA + dequant groups (AWQ)
+constexpr int kGemmThreadsF16 = 192;     // producer + MMA + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
-constexpr int kTmemAStages = 4;          // 4 x 64 columns of fp16 A operand
+constexpr int kTmemAStages = 6;          // 6 x 64 columns of fp16 A operand (columns 128..511)
 constexpr int kTmemACol0 = 128;
 
 // nibble position of the i-th of 8 consecutive values inside a 32-bit word: (0,4,1,5,2,6,3,7).
@@ -146,6 +149,43 @@ __device__ __forceinline__ int sk_owner(long long u, long long U, long long P) {
     return (int)c;
 }
 
+// One 32-bit word of the packed stream = 8 consecutive k of one feature row, nibble i at position
+// (0,4,1,5,2,6,3,7)[i].  Nibbles p and p+4 are extracted together as an fp16 pair:
+//   p = 0: (w      & 0x000f000f) | 0x6400 = 1024 +    q      p = 1: (w      & 0x00f000f0) | 0x6400 = 1024 + 16 q
+//   p = 2: (w >> 8 & 0x000f000f) | 0x6400                     p = 3: (w >> 8 & 0x00f000f0) | 0x6400
+// then   even: (1024 + q) - (1024 + z)        odd: (1024 + 16 q) * (1/16) - (64 + z)
+// are both EXACT (q - z), and one multiply by the group scale rounds once: fp16((q - z) * s).
+template <uint32_t kMask>
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "n"(kMask), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void dequant_word(uint32_t w, uint32_t ce, uint32_t co, uint32_t s2, uint32_t* out) {
+    const uint32_t magic = 0x64006400u, sixteenth = 0x2C002C00u;   // 1024, 1/16
+    const uint32_t w8 = w >> 8;
+    const uint32_t neg_co = co ^ 0x80008000u;
+    out[0] = h2_mul(h2_sub(lop3_and_or<0x000f000fu>(w, magic), ce), s2);
+    out[1] = h2_mul(h2_fma(lop3_and_or<0x00f000f0u>(w, magic), sixteenth, neg_co), s2);
+    out[2] = h2_mul(h2_sub(lop3_and_or<0x000f000fu>(w8, magic), ce), s2);
+    out[3] = h2_mul(h2_fma(lop3_and_or<0x00f000f0u>(w8, magic), sixteenth, neg_co), s2);
+}
+
 struct GemmParams {
     const unsigned char* packed;   // AWQ stream (kAwq) -- else unused
     int M, K, N_total;             // N_total = output features (rows of W)
@@ -164,7 +204,7 @@ struct GemmParams {
 
 template <int MPAD>
 struct GemmCfg {
-    static constexpr int kStagesAwq = MPAD <= 32 ? 8 : (MPAD == 64 ? 6 : 4);
+    static constexpr int kStagesAwq = MPAD == 16 ? 10 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4));
     static constexpr int kStagesF16 = MPAD <= 32 ? 8 : (MPAD == 64 ? 6 : 4);
     static constexpr int kXBytesAwq = MPAD * 256;           // [2 atoms][MPAD][128 B]
     static constexpr int kXBytesF16 = MPAD * 128;           // [MPAD][128 B]
@@ -262,14 +302,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     unsigned char* s_w = s_x + kStages * kXBytes;                // kStages x kWStride
     __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStride);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes);
+    static_assert(kStages <= 16, "barrier block holds 16 stages");
     uint64_t* full = bars;                    // [kStages]
-    uint64_t* empty = bars + 8;               // [kStages]
-    uint64_t* a_full = bars + 16;             // [kTmemAStages]
-    uint64_t* a_empty = bars + 20;            // [kTmemAStages]
-    uint64_t* acc_full = bars + 24;
-    uint64_t* acc_empty = bars + 25;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 26);
-    int* s_flag = reinterpret_cast<int*>(bars + 27);
+    uint64_t* empty = bars + 16;              // [kStages]
+    uint64_t* a_full = bars + 32;             // [kTmemAStages]
+    uint64_t* a_empty = bars + 40;            // [kTmemAStages]
+    uint64_t* acc_full = bars + 48;
+    uint64_t* acc_empty = bars + 49;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 50);
+    int* s_flag = reinterpret_cast<int*>(bars + 51);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long U = (long long)p.tiles * p.units_per_tile, P = gridDim.x;
@@ -280,10 +321,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         if (!kAwq) tma_prefetch_desc(&tmap_w);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(full + i, 1);
-            mbar_init(empty + i, kAwq ? 9 : 1);
+            mbar_init(empty + i, kAwq ? 5 : 1);      // 4 dequant warps of one group + the MMA commit
         }
         for (int i = 0; i < kTmemAStages; ++i) {
-            mbar_init(a_full + i, 8);
+            mbar_init(a_full + i, 4);
             mbar_init(a_empty + i, 1);
         }
         mbar_init(acc_full, 1);
@@ -367,60 +408,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     } else {
         // ===================== dequant (AWQ) + epilogue warps =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may touch
-        const int khalf = (warp - 2) >> 2;           // 0: warps 2..5, 1: warps 6..9
-        const bool is_epi = warp < 6;
+        const int grp = (warp - 2) >> 2;             // dequant group 0..kDqGroups-1; group 0 also runs the epilogue
+        const bool is_epi = grp == 0;
         const int fl = q * 32 + lane;                // feature lane 0..127
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        Ring r, ra;
         int seg = 0;
         long long u = u_begin;
+        int mine = grp;                              // CTA-local index of this group's next unit
         while (u < u_end) {
             const int tile = (int)(u / p.units_per_tile);
             const long long tile_u0 = (long long)tile * p.units_per_tile;
             const long long seg_begin = u;
             const long long seg_end = min(u_end, tile_u0 + p.units_per_tile);
             if constexpr (kAwq) {
-                for (; u < seg_end; ++u) {
-                    mbar_wait(full + r.stage, r.phase);
-                    const unsigned char* rec = s_w + r.stage * kWStride;
-                    const uint4 w0 = *reinterpret_cast<const uint4*>(rec + ((khalf * 2 + 0) * kTileN + fl) * 16);
-                    const uint4 w1 = *reinterpret_cast<const uint4*>(rec + ((khalf * 2 + 1) * kTileN + fl) * 16);
+                const int seg_end_local = (int)(seg_end - u_begin);
+                for (; mine < seg_end_local; mine += kDqGroups) {
+                    const int st = mine % kStages, ph = (mine / kStages) & 1;
+                    const int ts = mine % kTmemAStages, pa = (mine / kTmemAStages) & 1;
+                    mbar_wait(full + st, ph);
+                    const unsigned char* rec = s_w + st * kWStride;
                     const uint32_t sbits = *reinterpret_cast<const unsigned short*>(rec + kRecScaleOff + fl * 2);
                     const uint32_t zw = *reinterpret_cast<const uint32_t*>(rec + kRecZeroOff + (fl >> 3) * 4);
-                    const uint32_t zh = 0x6400u | ((zw >> (4 * (fl & 7))) & 0xFu);      // fp16(1024 + z)
-                    const uint32_t z2u = zh | (zh << 16), s2u = sbits | (sbits << 16);
-                    const __half2 z2 = *reinterpret_cast<const __half2*>(&z2u);
-                    const __half2 s2 = *reinterpret_cast<const __half2*>(&s2u);
-                    uint32_t a[32];
-                    const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const uint32_t z = (zw >> (4 * (fl & 7))) & 0xFu;
+                    const uint32_t ce = (0x6400u | z) * 0x10001u;            // (1024 + z) x2
+                    const uint32_t co = (0x5400u | (z << 4)) * 0x10001u;     // (64 + z) x2
+                    const uint32_t s2 = sbits * 0x10001u;
+                    const uint32_t taddr = tmem_base + lane_addr + kTmemACol0 + ts * 64;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) {
+                    for (int c = 0; c < 4; ++c) {                            // 4 chunks of 32 k (16 TMEM columns)
+                        const uint4 w4 = *reinterpret_cast<const uint4*>(rec + (c * kTileN + fl) * 16);
+                        const uint32_t words[4] = {w4.x, w4.y, w4.z, w4.w};
+                        uint32_t a[16];
 #pragma unroll
-                        for (int pp = 0; pp < 4; ++pp) {
-                            uint32_t t = ((words[w] >> (4 * pp)) & 0x000f000fu) | 0x64006400u;   // (1024+q_lo, 1024+q_hi)
-                            __half2 h = __hsub2(*reinterpret_cast<__half2*>(&t), z2);              // exact q - z
-                            h = __hmul2(h, s2);                                                    // one rounding
-                            a[w * 4 + pp] = *reinterpret_cast<uint32_t*>(&h);
+                        for (int w = 0; w < 4; ++w) dequant_word(words[w], ce, co, s2, &a[w * 4]);
+                        if (c == 0) {            // the MMA that last read this TMEM stage must have retired
+                            mbar_wait(a_empty + ts, pa ^ 1);
+                            tc_fence_after();
                         }
+                        UMB_TMEM_ST_X16(taddr + c * 16, a);
                     }
-                    mbar_wait(a_empty + ra.stage, ra.phase ^ 1);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + lane_addr + kTmemACol0 + ra.stage * 64 + khalf * 32;
-                    UMB_TMEM_ST_X16(taddr, (&a[0]));
-                    UMB_TMEM_ST_X16(taddr + 16, (&a[16]));
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        mbar_arrive(a_full + ra.stage);
-                        mbar_arrive(empty + r.stage);
+                        mbar_arrive(a_full + ts);
+                        mbar_arrive(empty + st);
                     }
-                    r.advance(kStages);
-                    ra.advance(kTmemAStages);
                 }
-            } else {
-                u = seg_end;
             }
+            u = seg_end;
             if (is_epi) {
                 const bool whole = (seg_begin == tile_u0) && (seg_end == tile_u0 + p.units_per_tile);
                 mbar_wait(acc_full, seg & 1);
@@ -650,7 +686,7 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmP
         UMB_CUDA(cudaFuncSetAttribute(gemm_kernel<MPAD, kAwq>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    gemm_kernel<MPAD, kAwq><<<grid, kGemmThreads, smem, st>>>(tx, tw, p);
+    gemm_kernel<MPAD, kAwq><<<grid, kAwq ? kGemmThreads : kGemmThreadsF16, smem, st>>>(tx, tw, p);
     count_launches(1);
     UMB_LAUNCH_CHECK();
     return UMB_OK;

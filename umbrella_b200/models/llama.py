@@ -141,7 +141,7 @@ class Llama:
         lib = _lib.load()
         self._gemm_ws = torch.zeros(lib.umb_llama_gemm_ws_bytes(H, I, Hq, Hkv, D, sh.vocab_size), dtype=torch.uint8,
                                     device=dev)
-        self._attn_ws = torch.empty(lib.umb_tree_attn_workspace_bytes(MAX_ROWS, Hq, D, self.max_length),
+        self._attn_ws = torch.zeros(lib.umb_tree_attn_workspace_bytes(MAX_ROWS, Hq, D, self.max_length),
                                     dtype=torch.uint8, device=dev)
         self._argmax_keys = torch.zeros(MAX_ROWS, dtype=torch.int64, device=dev)
         self.layer_weights = [None] * self.num_layers
@@ -261,19 +261,22 @@ class Llama:
         return logits.unsqueeze(0)
 
     @torch.inference_mode()
-    def prefill_forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, last_only: bool = True):
+    def prefill_forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, last_only: bool = True,
+                        want_logits: bool = True):
         """Causal forward over new rows appended at kv_offset; logits of the last row only by default
         (the engines use nothing else, static_speculation_engine.py:172)."""
         rows = input_ids.numel()
         m = ops.make_mask(ops.UMB_MASK_CAUSAL, prefix_len=self.kv_cache.kv_offset)
-        return self._forward(input_ids, position_ids, m, logits_from=rows - 1 if last_only else 0)
+        return self._forward(input_ids, position_ids, m, logits_from=rows - 1 if last_only else 0,
+                             want_logits=want_logits)
 
     @torch.inference_mode()
     def verify_forward(self, input_ids: torch.Tensor, position_ids: torch.Tensor, prefix_len: int,
-                       tree_bits: torch.Tensor, argmax_keys: torch.Tensor | None = None):
-        """Fast path of verify(): the mask is (prefix_len, ancestor bitmask), never materialised."""
+                       tree_bits: torch.Tensor, argmax_keys: torch.Tensor | None = None, want_logits: bool = True):
+        """Fast path of verify() and of the draft's per-level forward: the mask is (prefix_len, ancestor
+        bitmask rows), never materialised."""
         m = ops.make_mask(ops.UMB_MASK_TREE, prefix_len=prefix_len, tree_bits=tree_bits)
-        return self._forward(input_ids, position_ids, m, argmax_keys=argmax_keys)
+        return self._forward(input_ids, position_ids, m, argmax_keys=argmax_keys, want_logits=want_logits)
 
     # ------------------------------------------------------------------ cache ops (llama.py:136-142)
     def gather_kv_incremental(self, indices, offset: int):

@@ -165,7 +165,7 @@ def make_mask(mode: int, prefix_len: int = 0, tree_bits: torch.Tensor | None = N
 
 
 def tree_attn_workspace(qo: int, Hq: int, D: int, device) -> torch.Tensor:
-    return torch.empty(_lib.load().umb_tree_attn_workspace_bytes(qo, Hq, D, 0), dtype=torch.uint8, device=device)
+    return torch.zeros(_lib.load().umb_tree_attn_workspace_bytes(qo, Hq, D, 0), dtype=torch.uint8, device=device)
 
 
 def tree_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: int, mask: AttnMask,

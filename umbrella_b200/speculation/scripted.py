@@ -1,0 +1,49 @@
+"""Scripted acceptance for benchmarks on synthetic weights.
+
+Random-init draft and target models are uncorrelated, so "accepted tokens/sec" would degenerate to
+one token per verify.  The script replaces the target's sampled token at every tree node, AFTER the
+full target forward + arg-max has run (nothing is skipped in the timed region): with probability
+``acc[r]`` the node's rank-r child is declared the target's choice (its draft token is copied), else
+the target's own arg-max token is kept (which matches no child, up to chance).  The choices are
+drawn up front from a seeded generator, so two implementations fed the same seed see the same
+acceptance pattern.  ``acc`` defaults to the reference's DEFAULT_ACC (umbrella/sequoia_utils.py:7).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..sequoia_utils import DEFAULT_ACC
+
+
+class ScriptedAcceptance:
+    def __init__(self, successors, seed: int, max_iters: int, device, acc=None):
+        acc = DEFAULT_ACC if acc is None else acc
+        rng = np.random.default_rng(seed)
+        n = len(successors)
+        choice = np.full((max_iters, n), -1, dtype=np.int64)
+        u = rng.random((max_iters, n))
+        for v, kids in enumerate(successors):
+            c = 0.0
+            lo = np.zeros(max_iters)
+            for r, child in enumerate(kids):
+                if r >= len(acc):
+                    break
+                hi = lo + acc[r]
+                choice[(u[:, v] >= lo) & (u[:, v] < hi), v] = child
+                lo = hi
+        self.choice = torch.from_numpy(choice).to(device)
+        self.it = 0
+        self.max_iters = max_iters
+
+    def reset(self):
+        self.it = 0
+
+    def __call__(self, engine, sampled: torch.Tensor) -> torch.Tensor:
+        row = self.choice[self.it % self.max_iters]
+        self.it += 1
+        n = engine.num_nodes
+        tree_tokens = engine.tokens[0, n:n + row.numel()]
+        picked = tree_tokens.gather(0, row.clamp(min=0))
+        self.last = torch.where(row >= 0, picked, sampled)      # kept for tests / cross-implementation replay
+        return self.last

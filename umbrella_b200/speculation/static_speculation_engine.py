@@ -1,0 +1,350 @@
+"""StaticSpeculationEngine: Sequoia static-tree speculative decoding on the sm_100a verify path.
+
+Host-side mirror of reference umbrella/speculation/static_speculation_engine.py (same constructor
+kwargs, same 13-method BaseEngine surface, same return values and bookkeeping), with the inner loop
+replaced:
+
+  * verify(): one native target forward over the token tree (umb_llama_forward: AWQ tcgen05 GEMMs,
+    tree attention with (prefix_len, ancestor bitmask) instead of the O(S^2) master mask, arg-max
+    fused into the lm_head epilogue), then ONE accept kernel (umb_tree_accept: accept flags, path
+    compaction, token/position writes, EOS truncation, state advance) and ONE gather kernel per
+    model (umb_kv_gather); the host reads back 4 ints per iteration from pinned memory.
+  * no ``attn_mask`` [S, 2S], no per-step mask ``.contiguous()`` copy (static...:55-57,345), no
+    ``nonzero()`` / ``.tolist()`` syncs (:320,:330).
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from .. import ops
+from ..models.auto_model import AutoModelLM
+from ..sequoia_utils import load_growmap, tree_bits_from_mask
+from .base import BaseEngine
+from .speculation_utils import apply_repetition_penalty, apply_topk, is_sentence_complete_regex
+
+
+class StaticSpeculationEngine(BaseEngine):
+
+    def __init__(self, draft_model_name: str, target_model_name: str, dtype=torch.float16, device: str = "cuda:0",
+                 **kwargs) -> None:
+        self.draft_model_name = draft_model_name
+        self.target_model_name = target_model_name
+        self.dtype = dtype
+        self.device = device
+        self.growmap_path = kwargs.pop("growmap_path", None)
+        assert self.growmap_path is not None, "Please specify growmap path for static trees"
+        self.max_length = kwargs.pop("max_length", 8192)
+        self.stop_distance = kwargs.pop("stop_distance", 32)
+        self.safe_buffer = kwargs.pop("safe_buffer", 64)
+        self.temperature = kwargs.pop("temperature", 0.0)
+        self.topp = kwargs.pop("topp", 0.9)
+        self.repetition_penalty = kwargs.pop("repetition_penalty", 1.0)
+        self.topk = kwargs.pop("topk", 32)
+        self.config = kwargs
+        self.acceptance_script = None      # benchmark hook: callable(engine, sampled) -> sampled
+        self.draft_model = None
+        self.target_model = None
+        self.stats = {"verify_calls": 0}
+
+    # ------------------------------------------------------------------ set-up (static...:48-131)
+    def initialize(self, draft_model=None, target_model=None):
+        dev = self.device
+        self.growmap = load_growmap(self.growmap_path)
+        self.storage_ids = torch.arange(self.max_length, device=dev)
+        self.tokens = torch.zeros(1, self.max_length, dtype=torch.int64, device=dev)
+        self.position_ids = torch.zeros(1, self.max_length, dtype=torch.int64, device=dev)
+
+        idx_lists = self.growmap["roots"]
+        self.tree_depth = len(idx_lists)
+        self.level_ranges = [(lvl[0], lvl[-1] + 1) for lvl in idx_lists]      # levels are contiguous id ranges
+        for (a, b), lvl in zip(self.level_ranges, idx_lists):
+            assert list(range(a, b)) == list(lvl), "growmap levels must be contiguous node ranges"
+        self.Successors = self.growmap["Successors"]
+        self.tree_size = self.growmap["size"]
+        tree_mask = torch.tensor(self.growmap["mask"]) == 1
+        self.tree_mask = tree_mask.to(dev)
+        self.node_in_path = self.tree_mask.int().sum(dim=-1)
+        self.tree_bits = torch.from_numpy(tree_bits_from_mask(tree_mask.numpy())).to(dev)
+        parents = torch.zeros(self.tree_size, dtype=torch.int32)
+        for v, succ in enumerate(self.Successors):
+            for c in succ:
+                parents[c] = v
+        self.parents = parents.to(dev)
+        self.depth = torch.tensor(self.growmap["depth"], dtype=torch.int32, device=dev)
+        self.depth64 = self.depth.to(torch.int64)
+        self.branch_lists = self.growmap["branches"]
+
+        kw = dict(batch_size=1, max_length=self.max_length, device=dev, dtype=self.dtype)
+        if draft_model is None:
+            draft_model = AutoModelLM.from_pretrained(model_name=self.draft_model_name, offload=False, cuda_graph=True, **kw)
+            draft_model.alloc(**self.config)
+        if target_model is None:
+            target_model = AutoModelLM.from_pretrained(model_name=self.target_model_name, offload=False, **kw)
+            target_model.alloc(**self.config)
+        self.draft_model, self.target_model = draft_model, target_model
+
+        try:   # tokenizer / generation config need local HF files; token-id entry points work without
+            from transformers import AutoTokenizer
+            self.tokenizer = AutoTokenizer.from_pretrained(self.target_model_name, local_files_only=True)
+        except Exception:
+            self.tokenizer = None
+        self.vocab_size = self.target_model.config.vocab_size
+        self.eos_tokens = list(self.target_model.eos_tokens)
+        self.num_nodes = 0
+
+        # per-level gather of the draft's top-k samples (static...:115-123)
+        self.sample_gather_indices = {}
+        for i in range(self.tree_depth - 1):
+            width = max(self.branch_lists[i])
+            idx = [torch.arange(b, dtype=torch.long) + j * width for j, b in enumerate(self.branch_lists[i])]
+            self.sample_gather_indices[i] = torch.cat(idx).to(dev)
+
+        N = self.tree_size
+        self._argmax_keys = torch.zeros(max(N, 1), dtype=torch.int64, device=dev)
+        self._result = torch.zeros(4 + N, dtype=torch.int32, device=dev)
+        self._result_host = torch.zeros(4 + N, dtype=torch.int32).pin_memory()
+        self._set_eos(self.eos_tokens)
+        self.uniform_samples = torch.rand(3, N, device=dev)
+
+    def _set_eos(self, eos_tokens):
+        self.eos_tokens = list(eos_tokens)
+        self._eos_dev = torch.tensor(self.eos_tokens, dtype=torch.int64, device=self.device) if self.eos_tokens else None
+
+    # ------------------------------------------------------------------ prefill / append (static...:133-209)
+    def _encode(self, text):
+        if self.tokenizer is None:
+            raise RuntimeError("no tokenizer available offline: use _prefill/_append/generate(input_ids=...)")
+        return self.tokenizer.encode(text=text, return_tensors="pt").to(device=self.device)
+
+    def prefill(self, text: str):
+        return self._prefill(input_ids=self._encode(text))
+
+    def append(self, text: str):
+        return self._append(self._encode(text)[:, 1:])
+
+    @torch.inference_mode()
+    def _prefill(self, input_ids: torch.LongTensor):
+        prefix_len = input_ids.shape[1]
+        if prefix_len >= self.max_length - 2 * self.safe_buffer:
+            return False
+        self.num_nodes += prefix_len
+        self.num_nodes_this_iter = self.num_nodes + self.tree_size
+        self.num_draft_tokens_this_iter = self.num_nodes
+        self.tokens[:, :prefix_len].copy_(input_ids)
+        self.position_ids[:, :prefix_len] = torch.arange(prefix_len, device=self.device).unsqueeze(0)
+        self.position_ids[:, prefix_len:prefix_len + self.tree_size] = prefix_len + self.depth64
+        ids, pos = self.tokens[0, :prefix_len], self.position_ids[0, :prefix_len]
+        self.draft_model.prefill_forward(ids, pos, want_logits=False)
+        logits = self.target_model.prefill_forward(ids, pos, last_only=True)
+        self.tokens[0, self.num_nodes] = ops.argmax(logits)[0]
+        return True
+
+    @torch.inference_mode()
+    def _append(self, input_ids: torch.LongTensor):
+        append_len = input_ids.shape[1]
+        if append_len + self.num_nodes >= self.max_length - 2 * self.safe_buffer:
+            return False
+        self.tokens[:, self.num_nodes + 1:self.num_nodes + 1 + append_len].copy_(input_ids)
+        last = self.num_nodes
+        self.num_nodes += append_len + 1
+        self.num_nodes_this_iter = self.num_nodes + self.tree_size
+        self.num_draft_tokens_this_iter = self.num_nodes
+        self.position_ids[:, :self.num_nodes] = torch.arange(self.num_nodes, device=self.device).unsqueeze(0)
+        self.position_ids[:, self.num_nodes:self.num_nodes + self.tree_size] = self.num_nodes + self.depth64
+        ids, pos = self.tokens[0, last:self.num_nodes], self.position_ids[0, last:self.num_nodes]
+        self.draft_model.prefill_forward(ids, pos, want_logits=False)
+        logits = self.target_model.prefill_forward(ids, pos, last_only=True)
+        self.tokens[0, self.num_nodes] = ops.argmax(logits)[0]
+        return True
+
+    # ------------------------------------------------------------------ the loop
+    @torch.inference_mode()
+    def build_tree(self):
+        """Draft side (static...:257-281): one draft forward per tree level; the next level's tokens
+        are the per-node top-k draft tokens gathered in growmap order."""
+        n = self.num_nodes
+        for step in range(self.tree_depth):
+            a, b = self.level_ranges[step]
+            ids = self.tokens[0, n + a:n + b]
+            pos = self.position_ids[0, n + a:n + b]
+            last = step == self.tree_depth - 1
+            logits = self.draft_model.verify_forward(ids, pos, n, self.tree_bits[a:b], want_logits=not last)
+            self.num_draft_tokens_this_iter += b - a
+            if not last:
+                width = max(self.branch_lists[step])
+                new_tokens = logits.topk(k=width).indices.flatten().index_select(0, self.sample_gather_indices[step])
+                total = new_tokens.numel()
+                self.tokens[0, n + b:n + b + total] = new_tokens
+
+    def _sample_target(self, logits: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
+        """static...:298-310.  Greedy: decode the arg-max keys produced by the lm_head epilogue."""
+        n, N = self.num_nodes, self.tree_size
+        if self.repetition_penalty > 1.01:
+            logits = apply_repetition_penalty(self.tokens[:, :n + 1].expand(N, -1), logits, self.repetition_penalty)
+            ops.argmax_keys_to_ids(keys)              # drop (and reset) the un-penalised keys
+            if self.temperature < 0.05:
+                return ops.argmax(logits.contiguous())
+        if self.temperature < 0.05:
+            return ops.argmax_keys_to_ids(keys)
+        ops.argmax_keys_to_ids(keys)
+        # stochastic: top-k -> softmax(T) -> top-p renormalisation -> one sample per node
+        probs = torch.softmax(apply_topk(logits, self.topk) / self.temperature, dim=-1)
+        sp, si = probs.sort(dim=-1, descending=True)
+        keep = (sp.cumsum(-1) - sp) < self.topp
+        sp = sp * keep
+        pick = torch.multinomial(sp / sp.sum(-1, keepdim=True), 1)
+        return si.gather(-1, pick).squeeze(-1)
+
+    @torch.inference_mode()
+    def verify(self):
+        n, N = self.num_nodes, self.tree_size
+        ids = self.tokens[0, n:n + N]
+        pos = self.position_ids[0, n:n + N]
+        logits = self.target_model.verify_forward(ids, pos, n, self.tree_bits, argmax_keys=self._argmax_keys)
+        sampled = self._sample_target(logits, self._argmax_keys[:N])
+        if self.acceptance_script is not None:
+            sampled = self.acceptance_script(self, sampled)
+        ops.tree_accept(sampled, self.tokens[0], self.position_ids[0], self.parents, self.depth, n, self._eos_dev,
+                        self._result)
+        # compaction reads (len, path) from the device result; the host only needs 4 ints afterwards
+        self.draft_model.kv_cache.gather_from_result(self._result, n, 0)
+        self.target_model.kv_cache.gather_from_result(self._result, n, 0)
+        self._result_host.copy_(self._result, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        accept_length, cont, new_n = (int(x) for x in self._result_host[:3])
+        self.draft_model.kv_cache.kv_offset = n + accept_length
+        self.target_model.kv_cache.kv_offset = n + accept_length
+        self.num_nodes = new_n
+        self.num_draft_tokens_this_iter = new_n
+        self.num_nodes_this_iter = new_n + N
+        self.stats["verify_calls"] += 1
+        self.last_accept_length = accept_length
+        return bool(cont)
+
+    @torch.inference_mode()
+    def reset(self):
+        self.num_nodes = 0
+        self.tokens.zero_()
+        self.position_ids.zero_()
+        self.draft_model.clear()
+        self.target_model.clear()
+
+    def validate_status(self):
+        return self.num_nodes <= (self.max_length - self.safe_buffer)
+
+    def update_generation_args(self, **generation_args):
+        self.temperature = generation_args.pop("temperature", self.temperature)
+        self.topp = generation_args.pop("topp", self.topp)
+        self.repetition_penalty = generation_args.pop("repetition_penalty", self.repetition_penalty)
+        self.topk = generation_args.pop("topk", self.topk)
+
+    def _decode(self, ids):
+        if self.tokenizer is None:
+            return ""
+        return self.tokenizer.decode(ids, skip_special_tokens=True, clean_up_tokenization_spaces=False)
+
+    @torch.inference_mode()
+    def speculative_decoding(self, max_new_tokens=128):
+        """static...:211-255 -> (dec_len, seconds, large_model_steps)."""
+        max_new_tokens = max(max_new_tokens, self.stop_distance)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        steps, decode, start = 0, True, self.num_nodes
+        generated_ids, pos = [], 0
+        while decode and self.validate_status():
+            begin = self.num_nodes
+            self.build_tree()
+            decode = self.verify()
+            steps += 1
+            generated_ids.extend(self.tokens[0, begin:self.num_nodes].tolist())
+            text = self._decode(generated_ids).strip().split(" ")
+            now = len(text) - 1
+            if now > pos:
+                print(" ".join(text[pos:now]), end=" ", flush=True)
+                pos = now
+            done_len = self.num_nodes - start
+            if (is_sentence_complete_regex(text[-1]) and done_len >= max_new_tokens - self.stop_distance) \
+                    or done_len >= max_new_tokens:
+                decode = False
+        torch.cuda.synchronize()
+        t2 = time.time()
+        return self.num_nodes - start + 1, t2 - t1, steps
+
+    def _empty(self, api_args):
+        api_args.update(generated_text="", generated_tokens=[], avg_accept_tokens=0, time_per_output_token=0)
+        return api_args
+
+    @torch.inference_mode()
+    def generate(self, **api_args):
+        """static...:373-434: prefill (text or token ids), decode loop, stats, reset."""
+        self.update_generation_args(**api_args)
+        input_ids = api_args.get("input_ids", None)
+        max_new_tokens = api_args.get("max_new_tokens", 128)
+        if input_ids is None:
+            context = api_args.get("context", None)
+            if context is None or len(context) == 0 or max_new_tokens == 0:
+                return self._empty(api_args)
+            success = self.prefill(context)
+        else:
+            if len(input_ids) == 0 or max_new_tokens == 0:
+                return self._empty(api_args)
+            ids = torch.as_tensor(input_ids, dtype=torch.int64)
+            if not ids.is_cuda:
+                ids = ids.pin_memory().to(self.device, non_blocking=True) if torch.cuda.is_available() else ids
+            success = self._prefill(input_ids=ids.reshape(1, -1))
+        if not success:
+            self.reset()
+            return self._empty(api_args)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        steps, decode, start = 0, True, self.num_nodes
+        while decode and (self.num_nodes - start) < max_new_tokens and self.validate_status():
+            self.build_tree()
+            decode = self.verify()
+            steps += 1
+        torch.cuda.synchronize()
+        t2 = time.time()
+        dec_len = self.num_nodes - start + 1
+        out_ids = self.tokens[0, start:self.num_nodes + 1].tolist()
+        api_args["generated_text"] = self._decode(out_ids)
+        api_args["generated_tokens"] = out_ids
+        api_args["avg_accept_tokens"] = dec_len / max(steps, 1)
+        api_args["time_per_output_token"] = 1000 * (t2 - t1) / dec_len
+        api_args["large_model_steps"] = steps
+        api_args["decode_seconds"] = t2 - t1
+        self.reset()
+        return api_args
+
+    @torch.inference_mode()
+    def generate_stream(self, **api_args):
+        """static...:437-551: yields (partial_text, perf_log) after every verify."""
+        self.update_generation_args(**api_args)
+        input_ids = api_args.get("input_ids", None)
+        max_new_tokens = api_args.get("max_new_tokens", 128)
+        if input_ids is None:
+            context = api_args.get("context", None)
+            if not context or max_new_tokens == 0:
+                yield "", ""
+                return
+            success = self.prefill(context)
+        else:
+            ids = torch.as_tensor(input_ids, dtype=torch.int64).to(self.device)
+            success = self._prefill(input_ids=ids.reshape(1, -1))
+        if not success:
+            self.reset()
+            yield "", ""
+            return
+        torch.cuda.synchronize()
+        t1 = time.time()
+        steps, decode, start = 0, True, self.num_nodes
+        while decode and (self.num_nodes - start) < max_new_tokens and self.validate_status():
+            self.build_tree()
+            decode = self.verify()
+            steps += 1
+            dec_len = self.num_nodes - start + 1
+            dt = time.time() - t1
+            perf = "Avg Accept Tokens {:.2f} | TPOT {:.2f} ms".format(dec_len / steps, 1000 * dt / dec_len)
+            yield self._decode(self.tokens[0, start:self.num_nodes + 1].tolist()), perf
+        self.reset()
