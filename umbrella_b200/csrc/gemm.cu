@@ -25,6 +25,7 @@
 // ranges (one persistent CTA per SM), partial tiles are reduced through a small fp32 workspace in a
 // fixed order by the last-arriving CTA, so results are deterministic.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -200,6 +201,8 @@ struct GemmParams {
     unsigned long long* argmax;
     int* counters;                 // [tiles]
     float* slots;                  // [tiles + grid][MPAD][128]
+    int stages;                    // depth of the shared-memory ring
+    int debug;                     // UMB_GEMM_DEBUG bit-flags (profiling experiments only; 0 in production)
 };
 
 template <int MPAD>
@@ -211,10 +214,14 @@ struct GemmCfg {
     static constexpr int kWBytesF16 = kTileN * 128;         // [128][128 B]
     static constexpr int kPackedStride = 8576;              // record padded to a 128-byte multiple
     static constexpr int kExchBytes = MPAD * 64 * 2;
+    // Independent fp32 accumulators in TMEM (columns a * MPAD): consecutive k-steps rotate through them so
+    // that back-to-back tcgen05.mma never wait on each other's accumulate (a dependent 128xNx16 MMA chain
+    // runs at its ~150-cycle latency, not at its 8-cycle issue rate); the epilogue sums them.
+    static constexpr int kNumAcc = MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : (MPAD == 64 ? 2 : 1));
     static constexpr int kBarBytes = 512;
-    static constexpr int smem_bytes(bool awq) {
+    static constexpr int smem_bytes(bool awq, int stages) {
         return 1024 /*align slack*/ + kBarBytes + kExchBytes +
-               (awq ? kStagesAwq * (kXBytesAwq + kPackedStride) : kStagesF16 * (kXBytesF16 + kWBytesF16));
+               stages * (awq ? (kXBytesAwq + kPackedStride) : (kXBytesF16 + kWBytesF16));
     }
 };
 
@@ -285,16 +292,36 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
     }
 }
 
+// v[j] = sum over the kAcc accumulators of column (m0 + j); fixed order -> deterministic
+template <int kAcc, int MPAD>
+__device__ __forceinline__ void load_acc_sum(uint32_t taddr, float (&v)[16]) {
+    uint32_t rr[16];
+    UMB_TMEM_LD_X16(taddr, rr);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+#pragma unroll
+    for (int a = 1; a < kAcc; ++a) {
+        UMB_TMEM_LD_X16(taddr + a * MPAD, rr);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(rr[j]);
+    }
+}
+
 template <int MPAD, bool kAwq>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
     using Cfg = GemmCfg<MPAD>;
-    constexpr int kStages = kAwq ? Cfg::kStagesAwq : Cfg::kStagesF16;
+    const int kStages = p.stages;
     constexpr int kXBytes = kAwq ? Cfg::kXBytesAwq : Cfg::kXBytesF16;
     constexpr int kWStride = kAwq ? Cfg::kPackedStride : Cfg::kWBytesF16;
     constexpr uint32_t kTxBytes = kAwq ? (uint32_t)(kRecordBytes + kXBytes) : (uint32_t)(Cfg::kWBytesF16 + kXBytes);
     constexpr uint32_t kIdesc = umma_idesc_f16(kTileN, MPAD);
+    constexpr int kNumAcc = Cfg::kNumAcc;
+    constexpr int kNumAccF16 = kNumAcc < 4 ? kNumAcc : 4;      // 4 k-steps per fp16 unit
+    constexpr int kAccUsed = kAwq ? kNumAcc : kNumAccF16;
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -302,7 +329,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     unsigned char* s_w = s_x + kStages * kXBytes;                // kStages x kWStride
     __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStride);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes);
-    static_assert(kStages <= 16, "barrier block holds 16 stages");
     uint64_t* full = bars;                    // [kStages]
     uint64_t* empty = bars + 16;              // [kStages]
     uint64_t* a_full = bars + 32;             // [kTmemAStages]
@@ -341,67 +367,92 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+        {
             const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
             Ring r;
-            for (long long u = u_begin; u < u_end; ++u) {
-                const int tile = (int)(u / p.units_per_tile), g = (int)(u % p.units_per_tile);
-                mbar_wait(empty + r.stage, r.phase ^ 1);
-                mbar_arrive_expect_tx(full + r.stage, kTxBytes);
-                unsigned char* xs = s_x + r.stage * kXBytes;
-                if constexpr (kAwq) {
-                    tma_bulk_g2s(s_w + r.stage * kWStride, p.packed + u * kRecordBytes, kRecordBytes, full + r.stage, pol_w);
-                    tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full + r.stage, pol_x);
-                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full + r.stage, pol_x);
-                } else {
-                    tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full + r.stage, pol_w);
-                    tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full + r.stage, pol_x);
+            int tile = (int)u_begin / p.units_per_tile, g = (int)u_begin % p.units_per_tile;   // one 32-bit division, then incremental
+            const int n_units = (int)(u_end - u_begin);
+            const unsigned char* src = p.packed + (kAwq ? u_begin * kRecordBytes : 0);
+            for (int i = 0; i < n_units; ++i, ++g) {
+                if (g == p.units_per_tile) {
+                    g = 0;
+                    ++tile;
                 }
+                mbar_wait(empty + r.stage, r.phase ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(full + r.stage, (kAwq && (p.debug & 16)) ? (uint32_t)kRecordBytes : kTxBytes);
+                    unsigned char* xs = s_x + r.stage * kXBytes;
+                    if constexpr (kAwq) {
+                        tma_bulk_g2s(s_w + r.stage * kWStride, src, kRecordBytes, full + r.stage, pol_w);
+                        if (!(p.debug & 16)) {
+                            tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full + r.stage, pol_x);
+                            tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full + r.stage, pol_x);
+                        }
+                    } else {
+                        tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full + r.stage, pol_w);
+                        tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full + r.stage, pol_x);
+                    }
+                }
+                __syncwarp();
+                src += kRecordBytes;
                 r.advance(kStages);
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+        {
             Ring r, ra;
             int seg = 0;
-            long long u = u_begin;
-            while (u < u_end) {
-                const int tile = (int)(u / p.units_per_tile);
-                const long long seg_end = min(u_end, (long long)(tile + 1) * p.units_per_tile);
+            int u = 0;                                                  // CTA-local unit index
+            const int n_units = (int)(u_end - u_begin);
+            int in_tile = (int)u_begin % p.units_per_tile;              // position of the next unit inside its tile
+            constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+            while (u < n_units) {
+                const int seg_len = min(n_units - u, p.units_per_tile - in_tile);
                 mbar_wait(acc_empty, (seg & 1) ^ 1);
                 tc_fence_after();
-                bool first = true;
-                for (; u < seg_end; ++u) {
+                for (int j = 0; j < seg_len; ++j) {
                     mbar_wait(full + r.stage, r.phase);
                     const uint32_t xs = smem_u32(s_x + r.stage * kXBytes);
+                    const uint64_t bd0 = kDescHi | (uint64_t)((xs & 0x3FFFF) >> 4);
                     if constexpr (kAwq) {
                         mbar_wait(a_full + ra.stage, ra.phase);
                         tc_fence_after();
                         const uint32_t a_col = tmem_base + kTmemACol0 + ra.stage * 64;
+                        if (elect_one()) {
+                            if (!(p.debug & 4)) {
 #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            const uint64_t bd = umma_smem_desc_sw128(xs + (kk >> 2) * (MPAD * 128) + (kk & 3) * 32);
-                            umma_ts_f16(tmem_base, a_col + kk * 8, bd, kIdesc, (first && kk == 0) ? 0u : 1u);
+                                for (int kk = 0; kk < 8; ++kk) {
+                                    const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (MPAD * 128) + (kk & 3) * 32) >> 4);
+                                    umma_ts_f16(tmem_base + (kk % kNumAcc) * MPAD, a_col + kk * 8, bd, kIdesc,
+                                                (j == 0 && kk < kNumAcc) ? 0u : 1u);
+                                }
+                            }
+                            umma_commit(a_empty + ra.stage);
+                            umma_commit(empty + r.stage);
+                            if (j == seg_len - 1) umma_commit(acc_full);
                         }
-                        umma_commit(a_empty + ra.stage);
+                        __syncwarp();
                         ra.advance(kTmemAStages);
                     } else {
                         tc_fence_after();
                         const uint32_t ws = smem_u32(s_w + r.stage * kWStride);
+                        const uint64_t ad0 = kDescHi | (uint64_t)((ws & 0x3FFFF) >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t ad = umma_smem_desc_sw128(ws + kk * 32);
-                            const uint64_t bd = umma_smem_desc_sw128(xs + kk * 32);
-                            umma_ss_f16(tmem_base, ad, bd, kIdesc, (first && kk == 0) ? 0u : 1u);
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_ss_f16(tmem_base + (kk % kNumAccF16) * MPAD, ad0 + kk * 2, bd0 + kk * 2, kIdesc,
+                                            (j == 0 && kk < kNumAccF16) ? 0u : 1u);
+                            umma_commit(empty + r.stage);
+                            if (j == seg_len - 1) umma_commit(acc_full);
                         }
+                        __syncwarp();
                     }
-                    umma_commit(empty + r.stage);
-                    first = false;
                     r.advance(kStages);
                 }
-                umma_commit(acc_full);
+                u += seg_len;
+                in_tile = 0;
                 ++seg;
             }
         }
@@ -415,16 +466,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         int seg = 0;
         long long u = u_begin;
         int mine = grp;                              // CTA-local index of this group's next unit
+        int dq_st = grp % kStages, dq_ph = 0, dq_ts = grp % kTmemAStages, dq_pa = 0;   // its ring positions
         while (u < u_end) {
-            const int tile = (int)(u / p.units_per_tile);
+            const int tile = (int)u / p.units_per_tile;
             const long long tile_u0 = (long long)tile * p.units_per_tile;
             const long long seg_begin = u;
             const long long seg_end = min(u_end, tile_u0 + p.units_per_tile);
             if constexpr (kAwq) {
                 const int seg_end_local = (int)(seg_end - u_begin);
                 for (; mine < seg_end_local; mine += kDqGroups) {
-                    const int st = mine % kStages, ph = (mine / kStages) & 1;
-                    const int ts = mine % kTmemAStages, pa = (mine / kTmemAStages) & 1;
+                    const int st = dq_st, ph = dq_ph, ts = dq_ts, pa = dq_pa;
+                    dq_st += kDqGroups;                      // this group's next unit is kDqGroups further on
+                    if (dq_st >= kStages) {
+                        dq_st -= kStages;
+                        dq_ph ^= 1;
+                    }
+                    dq_ts += kDqGroups;
+                    if (dq_ts >= kTmemAStages) {
+                        dq_ts -= kTmemAStages;
+                        dq_pa ^= 1;
+                    }
                     mbar_wait(full + st, ph);
                     const unsigned char* rec = s_w + st * kWStride;
                     const uint32_t sbits = *reinterpret_cast<const unsigned short*>(rec + kRecScaleOff + fl * 2);
@@ -439,13 +500,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         const uint4 w4 = *reinterpret_cast<const uint4*>(rec + (c * kTileN + fl) * 16);
                         const uint32_t words[4] = {w4.x, w4.y, w4.z, w4.w};
                         uint32_t a[16];
+                        if (p.debug & 1) {
 #pragma unroll
-                        for (int w = 0; w < 4; ++w) dequant_word(words[w], ce, co, s2, &a[w * 4]);
-                        if (c == 0) {            // the MMA that last read this TMEM stage must have retired
+                            for (int w = 0; w < 16; ++w) a[w] = words[w & 3];
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < 4; ++w) dequant_word(words[w], ce, co, s2, &a[w * 4]);
+                        }
+                        if (c == 0 && !(p.debug & 2)) {            // the MMA that last read this TMEM stage must have retired
                             mbar_wait(a_empty + ts, pa ^ 1);
                             tc_fence_after();
                         }
-                        UMB_TMEM_ST_X16(taddr + c * 16, a);
+                        if (!(p.debug & 8)) UMB_TMEM_ST_X16(taddr + c * 16, a);
+                        else if (a[3] == 0x12345678u) s_exch[0] = __float2half_rn(1.f);
                     }
                     tc_wait_st();
                     tc_fence_before();
@@ -464,17 +531,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 if (whole) {
 #pragma unroll 1
                     for (int m0 = 0; m0 < MPAD; m0 += 16) {
-                        uint32_t rr[16];
-                        UMB_TMEM_LD_X16(tmem_base + lane_addr + m0, rr);
-                        tc_wait_ld();
-                        if (m0 + 16 >= MPAD) {       // accumulator fully read: hand TMEM back to the MMA warp
+                        float v[16];
+                        load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v);
+                        if (m0 + 16 >= MPAD) {       // accumulators fully read: hand TMEM back to the MMA warp
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(acc_empty);
                         }
-                        float v[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
                         if (m0 < p.M || p.mode == UMB_EPI_SILU_MUL) epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
                     }
                 } else {
@@ -482,9 +545,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     float* slot = p.slots + ((size_t)tile + blockIdx.x) * (MPAD * kTileN);
 #pragma unroll 1
                     for (int m0 = 0; m0 < MPAD; m0 += 16) {
-                        uint32_t rr[16];
-                        UMB_TMEM_LD_X16(tmem_base + lane_addr + m0, rr);
-                        tc_wait_ld();
+                        float v[16];
+                        load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v);
                         if (m0 + 16 >= MPAD) {
                             tc_fence_before();
                             __syncwarp();
@@ -492,7 +554,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         }
                         if (m0 < p.M) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) slot[(m0 + j) * kTileN + fl] = __uint_as_float(rr[j]);
+                            for (int j = 0; j < 16; ++j) slot[(m0 + j) * kTileN + fl] = v[j];
                         }
                     }
                     __threadfence();
@@ -679,12 +741,21 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 static int mpad_of(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128)); }
 
 template <int MPAD, bool kAwq>
-static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const GemmParams& p, int grid, cudaStream_t st) {
-    const int smem = GemmCfg<MPAD>::smem_bytes(kAwq);
-    static bool attr_done = false;
-    if (!attr_done) {
+static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, GemmParams p, int grid, cudaStream_t st) {
+    p.stages = kAwq ? GemmCfg<MPAD>::kStagesAwq : GemmCfg<MPAD>::kStagesF16;
+    {
+        static int env_stages = -1;
+        if (env_stages < 0) {
+            const char* e = getenv("UMB_GEMM_STAGES");
+            env_stages = e ? atoi(e) : 0;
+        }
+        if (env_stages > 0 && env_stages <= 16 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024) p.stages = env_stages;
+    }
+    const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages);
+    static int attr_smem = 0;
+    if (attr_smem < smem) {
         UMB_CUDA(cudaFuncSetAttribute(gemm_kernel<MPAD, kAwq>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
+        attr_smem = smem;
     }
     gemm_kernel<MPAD, kAwq><<<grid, kAwq ? kGemmThreads : kGemmThreadsF16, smem, st>>>(tx, tw, p);
     count_launches(1);
@@ -714,12 +785,21 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     p.residual = epi ? (const __half*)epi->residual : nullptr;
     p.ld_residual = epi ? epi->ld_residual : 0;
     p.argmax = epi ? epi->argmax : nullptr;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("UMB_GEMM_DEBUG");
+            dbg = e ? atoi(e) : 0;
+        }
+        p.debug = dbg;
+    }
     UMB_CHECK_ARG(p.mode >= UMB_EPI_STORE && p.mode <= UMB_EPI_LOGITS);
     if (p.mode == UMB_EPI_RESIDUAL) UMB_CHECK_ARG(p.residual != nullptr);
     if (p.mode == UMB_EPI_SILU_MUL) UMB_CHECK_ARG((N_total % kTileN) == 0 && p.bias == nullptr);
 
     const int mpad = mpad_of(M);
     const long long U = (long long)p.tiles * p.units_per_tile;
+    if (U >= (1ll << 31)) return UMB_ERR_UNSUPPORTED;
     int grid = sm_count();
     if ((long long)grid > U) grid = (int)U;
     const size_t need = umb_gemm_workspace_bytes(M, K, N_total);
