@@ -162,29 +162,32 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "n"(kMask), "r"(c));
     return d;
 }
-__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ void dequant_word(uint32_t w, uint32_t ce, uint32_t co, uint32_t s2, uint32_t* out) {
-    const uint32_t magic = 0x64006400u, sixteenth = 0x2C002C00u;   // 1024, 1/16
+__device__ __forceinline__ __half2 as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+__device__ __forceinline__ uint32_t as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ void dequant_word(uint32_t w, uint32_t magic, __half2 ce, __half2 neg_co, __half2 s2,
+                                             uint32_t* out) {
+    const __half2 sixteenth = as_h2(0x2C002C00u);                 // 1/16
     const uint32_t w8 = w >> 8;
-    const uint32_t neg_co = co ^ 0x80008000u;
-    out[0] = h2_mul(h2_sub(lop3_and_or<0x000f000fu>(w, magic), ce), s2);
-    out[1] = h2_mul(h2_fma(lop3_and_or<0x00f000f0u>(w, magic), sixteenth, neg_co), s2);
-    out[2] = h2_mul(h2_sub(lop3_and_or<0x000f000fu>(w8, magic), ce), s2);
-    out[3] = h2_mul(h2_fma(lop3_and_or<0x00f000f0u>(w8, magic), sixteenth, neg_co), s2);
+    // (t - ce) and fma(t, 1/16, -co) are exact; the multiply by the scale is the single rounding
+    out[0] = as_u32(__hmul2(__hsub2(as_h2(lop3_and_or<0x000f000fu>(w, magic)), ce), s2));
+    out[1] = as_u32(__hmul2(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w, magic)), sixteenth, neg_co), s2));
+    out[2] = as_u32(__hmul2(__hsub2(as_h2(lop3_and_or<0x000f000fu>(w8, magic)), ce), s2));
+    out[3] = as_u32(__hmul2(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w8, magic)), sixteenth, neg_co), s2));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
 }
 
 struct GemmParams {
@@ -202,7 +205,6 @@ struct GemmParams {
     int* counters;                 // [tiles]
     float* slots;                  // [tiles + grid][MPAD][128]
     int stages;                    // depth of the shared-memory ring
-    int debug;                     // UMB_GEMM_DEBUG bit-flags (profiling experiments only; 0 in production)
 };
 
 template <int MPAD>
@@ -381,14 +383,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 }
                 mbar_wait(empty + r.stage, r.phase ^ 1);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(full + r.stage, (kAwq && (p.debug & 16)) ? (uint32_t)kRecordBytes : kTxBytes);
+                    mbar_arrive_expect_tx(full + r.stage, kTxBytes);
                     unsigned char* xs = s_x + r.stage * kXBytes;
                     if constexpr (kAwq) {
                         tma_bulk_g2s(s_w + r.stage * kWStride, src, kRecordBytes, full + r.stage, pol_w);
-                        if (!(p.debug & 16)) {
-                            tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full + r.stage, pol_x);
-                            tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full + r.stage, pol_x);
-                        }
+                        tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full + r.stage, pol_x);
+                        tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full + r.stage, pol_x);
                     } else {
                         tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full + r.stage, pol_w);
                         tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full + r.stage, pol_x);
@@ -421,13 +421,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         tc_fence_after();
                         const uint32_t a_col = tmem_base + kTmemACol0 + ra.stage * 64;
                         if (elect_one()) {
-                            if (!(p.debug & 4)) {
 #pragma unroll
-                                for (int kk = 0; kk < 8; ++kk) {
-                                    const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (MPAD * 128) + (kk & 3) * 32) >> 4);
-                                    umma_ts_f16(tmem_base + (kk % kNumAcc) * MPAD, a_col + kk * 8, bd, kIdesc,
-                                                (j == 0 && kk < kNumAcc) ? 0u : 1u);
-                                }
+                            for (int kk = 0; kk < 8; ++kk) {
+                                const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (MPAD * 128) + (kk & 3) * 32) >> 4);
+                                umma_ts_f16(tmem_base + (kk % kNumAcc) * MPAD, a_col + kk * 8, bd, kIdesc,
+                                            (j == 0 && kk < kNumAcc) ? 0u : 1u);
                             }
                             umma_commit(a_empty + ra.stage);
                             umma_commit(empty + r.stage);
@@ -487,32 +485,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         dq_pa ^= 1;
                     }
                     mbar_wait(full + st, ph);
-                    const unsigned char* rec = s_w + st * kWStride;
-                    const uint32_t sbits = *reinterpret_cast<const unsigned short*>(rec + kRecScaleOff + fl * 2);
-                    const uint32_t zw = *reinterpret_cast<const uint32_t*>(rec + kRecZeroOff + (fl >> 3) * 4);
+                    const uint32_t rec = smem_u32(s_w + st * kWStride);
+                    uint4 w4[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) w4[c] = lds128(rec + (c * kTileN + fl) * 16);    // 128 k of this feature row
+                    const uint32_t sbits = lds16(rec + kRecScaleOff + fl * 2);
+                    const uint32_t zw = lds32(rec + kRecZeroOff + (fl >> 3) * 4);
                     const uint32_t z = (zw >> (4 * (fl & 7))) & 0xFu;
-                    const uint32_t ce = (0x6400u | z) * 0x10001u;            // (1024 + z) x2
-                    const uint32_t co = (0x5400u | (z << 4)) * 0x10001u;     // (64 + z) x2
-                    const uint32_t s2 = sbits * 0x10001u;
+                    const __half2 ce = as_h2((0x6400u | z) * 0x10001u);                 // (1024 + z) x2
+                    const __half2 neg_co = as_h2((0xD400u | (z << 4)) * 0x10001u);      // -(64 + z) x2
+                    const __half2 s2 = as_h2(sbits * 0x10001u);
+                    const uint32_t magic = 0x64006400u;
                     const uint32_t taddr = tmem_base + lane_addr + kTmemACol0 + ts * 64;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {                            // 4 chunks of 32 k (16 TMEM columns)
-                        const uint4 w4 = *reinterpret_cast<const uint4*>(rec + (c * kTileN + fl) * 16);
-                        const uint32_t words[4] = {w4.x, w4.y, w4.z, w4.w};
+                        const uint32_t words[4] = {w4[c].x, w4[c].y, w4[c].z, w4[c].w};
                         uint32_t a[16];
-                        if (p.debug & 1) {
 #pragma unroll
-                            for (int w = 0; w < 16; ++w) a[w] = words[w & 3];
-                        } else {
-#pragma unroll
-                            for (int w = 0; w < 4; ++w) dequant_word(words[w], ce, co, s2, &a[w * 4]);
-                        }
-                        if (c == 0 && !(p.debug & 2)) {            // the MMA that last read this TMEM stage must have retired
+                        for (int w = 0; w < 4; ++w) dequant_word(words[w], magic, ce, neg_co, s2, &a[w * 4]);
+                        if (c == 0) {            // the MMA that last read this TMEM stage must have retired
                             mbar_wait(a_empty + ts, pa ^ 1);
                             tc_fence_after();
                         }
-                        if (!(p.debug & 8)) UMB_TMEM_ST_X16(taddr + c * 16, a);
-                        else if (a[3] == 0x12345678u) s_exch[0] = __float2half_rn(1.f);
+                        UMB_TMEM_ST_X16(taddr + c * 16, a);
                     }
                     tc_wait_st();
                     tc_fence_before();
@@ -785,14 +780,7 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     p.residual = epi ? (const __half*)epi->residual : nullptr;
     p.ld_residual = epi ? epi->ld_residual : 0;
     p.argmax = epi ? epi->argmax : nullptr;
-    {
-        static int dbg = -1;
-        if (dbg < 0) {
-            const char* e = getenv("UMB_GEMM_DEBUG");
-            dbg = e ? atoi(e) : 0;
-        }
-        p.debug = dbg;
-    }
+
     UMB_CHECK_ARG(p.mode >= UMB_EPI_STORE && p.mode <= UMB_EPI_LOGITS);
     if (p.mode == UMB_EPI_RESIDUAL) UMB_CHECK_ARG(p.residual != nullptr);
     if (p.mode == UMB_EPI_SILU_MUL) UMB_CHECK_ARG((N_total % kTileN) == 0 && p.bias == nullptr);
