@@ -34,15 +34,17 @@ namespace umb {
 
 constexpr int kTileN = 128;              // output features per tile (UMMA M)
 constexpr int kGroup = 128;              // AWQ group size == k per AWQ unit
-constexpr int kRecordBytes = 8512;       // 8192 nibble bytes + 256 scale bytes + 64 zero bytes
+constexpr int kRecordBytes = 8512;       // 8192 nibble bytes + 256 scale bytes + 64 zero bytes (what a TMA copy moves)
+#ifndef UMB_RECORD_STRIDE
+#define UMB_RECORD_STRIDE 8512
+#endif
+constexpr int kRecordStride = UMB_RECORD_STRIDE;   // distance between records in the stream
 constexpr int kRecScaleOff = 8192;
 constexpr int kRecZeroOff = 8448;
 constexpr int kDqGroups = 3;              // dequant warp groups (4 warps each, one per TMEM lane quarter)
-constexpr int kGemmThreads = 64 + 128 * kDqGroups;   // producer + MMA + dequant groups (AWQ)
-constexpr int kGemmThreadsF16 = 192;     // producer + MMA + 4 epilogue warps (fp16 weights)
+constexpr int kGemmThreads = 96 + 128 * kDqGroups;   // producer + 2 MMA issuers + dequant groups (AWQ)
+constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
-constexpr int kTmemAStages = 6;          // 6 x 64 columns of fp16 A operand (columns 128..511)
-constexpr int kTmemACol0 = 128;
 
 // nibble position of the i-th of 8 consecutive values inside a 32-bit word: (0,4,1,5,2,6,3,7).
 // Used by the AutoAWQ checkpoint layout (along N) and by our repacked stream (along K): nibbles p
@@ -76,7 +78,7 @@ __global__ void awq_repack_weights_kernel(const int32_t* __restrict__ qweight, i
         const int64_t pr = packed_row(c * 8 + j, row_block, row_stride, row_offset);
         const int64_t tile = pr / kTileN;
         const int r = (int)(pr % kTileN);
-        unsigned char* rec = packed + (tile * G + g) * kRecordBytes;
+        unsigned char* rec = packed + (tile * G + g) * kRecordStride;
         *reinterpret_cast<uint32_t*>(rec + ((kb * 2 + ch) * kTileN + r) * 16 + w * 4) = out;
     }
 }
@@ -94,7 +96,7 @@ __global__ void awq_repack_meta_kernel(const int32_t* __restrict__ qzeros, const
     const int64_t pr = packed_row(c * 8, row_block, row_stride, row_offset);   // 8-aligned run of rows
     const int64_t tile = pr / kTileN;
     const int r = (int)(pr % kTileN);
-    unsigned char* rec = packed + (tile * G + g) * kRecordBytes;
+    unsigned char* rec = packed + (tile * G + g) * kRecordStride;
     *reinterpret_cast<uint32_t*>(rec + kRecZeroOff + (r >> 3) * 4) = zout;
     *reinterpret_cast<uint4*>(rec + kRecScaleOff + r * 2) =
         *reinterpret_cast<const uint4*>(scales + (int64_t)g * N + c * 8);
@@ -128,7 +130,7 @@ __global__ void awq_unpack_kernel(const unsigned char* __restrict__ packed, int 
     const int k0 = kw * 8, g = k0 / kGroup, kk = k0 % kGroup;
     const int kb = kk >> 6, ch = (kk >> 5) & 1, w = (kk >> 3) & 3;
     const int tile = pr / kTileN, r = pr % kTileN;
-    const unsigned char* rec = packed + ((int64_t)tile * G + g) * kRecordBytes;
+    const unsigned char* rec = packed + ((int64_t)tile * G + g) * kRecordStride;
     const uint32_t word = *reinterpret_cast<const uint32_t*>(rec + ((kb * 2 + ch) * kTileN + r) * 16 + w * 4);
     const uint32_t zw = *reinterpret_cast<const uint32_t*>(rec + kRecZeroOff + (r >> 3) * 4);
     const int z = (int)((zw >> (4 * (r & 7))) & 0xFu);
@@ -205,6 +207,7 @@ struct GemmParams {
     int* counters;                 // [tiles]
     float* slots;                  // [tiles + grid][MPAD][128]
     int stages;                    // depth of the shared-memory ring
+    int prefetch;                  // L2 prefetch distance of the weight stream, in units (0 = off)
 };
 
 template <int MPAD>
@@ -219,7 +222,9 @@ struct GemmCfg {
     // Independent fp32 accumulators in TMEM (columns a * MPAD): consecutive k-steps rotate through them so
     // that back-to-back tcgen05.mma never wait on each other's accumulate (a dependent 128xNx16 MMA chain
     // runs at its ~150-cycle latency, not at its 8-cycle issue rate); the epilogue sums them.
-    static constexpr int kNumAcc = MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : (MPAD == 64 ? 2 : 1));
+    static constexpr int kNumAcc = MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : 2);
+    static constexpr int kTmemACol0 = kNumAcc * MPAD < 128 ? 128 : kNumAcc * MPAD;   // A operand stages start here
+    static constexpr int kTmemAStages = (kTmemCols - kTmemACol0) / 64;             // 6 (4 at MPAD = 128)
     static constexpr int kBarBytes = 512;
     static constexpr int smem_bytes(bool awq, int stages) {
         return 1024 /*align slack*/ + kBarBytes + kExchBytes +
@@ -294,16 +299,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
     }
 }
 
-// v[j] = sum over the kAcc accumulators of column (m0 + j); fixed order -> deterministic
+// v[j] = sum over the accumulators of column (m0 + j), in a fixed order (deterministic).  The
+// accumulators are split between the two MMA warps (first / second half); `use_mask` bit w tells
+// whether warp w issued anything into its half during this segment.
 template <int kAcc, int MPAD>
-__device__ __forceinline__ void load_acc_sum(uint32_t taddr, float (&v)[16]) {
+__device__ __forceinline__ void load_acc_sum(uint32_t taddr, float (&v)[16], int use_mask) {
     uint32_t rr[16];
-    UMB_TMEM_LD_X16(taddr, rr);
-    tc_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
 #pragma unroll
-    for (int a = 1; a < kAcc; ++a) {
+    for (int a = 0; a < kAcc; ++a) {
+        if (!((use_mask >> (a / (kAcc / 2))) & 1)) continue;
         UMB_TMEM_LD_X16(taddr + a * MPAD, rr);
         tc_wait_ld();
 #pragma unroll
@@ -311,6 +317,12 @@ __device__ __forceinline__ void load_acc_sum(uint32_t taddr, float (&v)[16]) {
     }
 }
 
+// Warp roles (AWQ: 15 warps, fp16: 7 warps)
+//   warp 0       TMA producer
+//   warps 1, 2   MMA issuers: CTA-local unit u is issued by warp 1 + (u & 1), each into its own half of
+//                the TMEM accumulators -- the per-unit issue loop (two mbarrier waits, 8 UTCHMMA, one
+//                commit) is the serial bottleneck of a one-issuer design at 8.5 KB units
+//   warps 3..14  dequant groups (AWQ); warps 3..6 also run the epilogue
 template <int MPAD, bool kAwq>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -321,9 +333,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     constexpr int kWStride = kAwq ? Cfg::kPackedStride : Cfg::kWBytesF16;
     constexpr uint32_t kTxBytes = kAwq ? (uint32_t)(kRecordBytes + kXBytes) : (uint32_t)(Cfg::kWBytesF16 + kXBytes);
     constexpr uint32_t kIdesc = umma_idesc_f16(kTileN, MPAD);
-    constexpr int kNumAcc = Cfg::kNumAcc;
-    constexpr int kNumAccF16 = kNumAcc < 4 ? kNumAcc : 4;      // 4 k-steps per fp16 unit
-    constexpr int kAccUsed = kAwq ? kNumAcc : kNumAccF16;
+    constexpr int kNumAcc = Cfg::kNumAcc;                       // >= 2, even
+    constexpr int kAccUsed = kAwq ? kNumAcc : (kNumAcc < 8 ? kNumAcc : 8);
+    constexpr int kAccHalf = kAccUsed / 2;                      // accumulators per MMA warp
+    constexpr int kACol0 = Cfg::kTmemACol0;
+    constexpr int kAStages = Cfg::kTmemAStages;
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -331,10 +345,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     unsigned char* s_w = s_x + kStages * kXBytes;                // kStages x kWStride
     __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStride);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes);
-    uint64_t* full = bars;                    // [kStages]
-    uint64_t* empty = bars + 16;              // [kStages]
-    uint64_t* a_full = bars + 32;             // [kTmemAStages]
-    uint64_t* a_empty = bars + 40;            // [kTmemAStages]
+    uint64_t* full = bars;                    // [kStages]   TMA landed (W record + x slab)
+    uint64_t* done = bars + 16;               // [kStages]   every MMA of the unit in this stage has retired
+    uint64_t* a_full = bars + 32;             // [kAStages]  dequantised A operand is in tensor memory
     uint64_t* acc_full = bars + 48;
     uint64_t* acc_empty = bars + 49;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 50);
@@ -343,19 +356,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long U = (long long)p.tiles * p.units_per_tile, P = gridDim.x;
     const long long u_begin = sk_begin(blockIdx.x, U, P), u_end = sk_begin(blockIdx.x + 1, U, P);
+    const int n_units = (int)(u_end - u_begin);
+    const int in_tile0 = (int)u_begin % p.units_per_tile;        // position of the first unit inside its tile
+    const int tile0 = (int)u_begin / p.units_per_tile;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_x);
         if (!kAwq) tma_prefetch_desc(&tmap_w);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(full + i, 1);
-            mbar_init(empty + i, kAwq ? 5 : 1);      // 4 dequant warps of one group + the MMA commit
+            mbar_init(done + i, 1);
         }
-        for (int i = 0; i < kTmemAStages; ++i) {
-            mbar_init(a_full + i, 4);
-            mbar_init(a_empty + i, 1);
-        }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < kAStages; ++i) mbar_init(a_full + i, 4);
+        mbar_init(acc_full, 2);
         mbar_init(acc_empty, 4);
         fence_barrier_init();
     }
@@ -370,120 +383,124 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
-        {
-            const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
-            Ring r;
-            int tile = (int)u_begin / p.units_per_tile, g = (int)u_begin % p.units_per_tile;   // one 32-bit division, then incremental
-            const int n_units = (int)(u_end - u_begin);
-            const unsigned char* src = p.packed + (kAwq ? u_begin * kRecordBytes : 0);
-            for (int i = 0; i < n_units; ++i, ++g) {
-                if (g == p.units_per_tile) {
-                    g = 0;
-                    ++tile;
+        const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
+        Ring r;
+        int tile = tile0, g = in_tile0;
+        const unsigned char* src = p.packed + (kAwq ? u_begin * kRecordStride : 0);
+        for (int i = 0; i < n_units; ++i, ++g) {
+            if (g == p.units_per_tile) {
+                g = 0;
+                ++tile;
+            }
+            mbar_wait(done + r.stage, r.phase ^ 1);              // the unit that last used this stage has retired
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full + r.stage, kTxBytes);
+                unsigned char* xs = s_x + r.stage * kXBytes;
+                if constexpr (kAwq) {
+                    tma_bulk_g2s(s_w + r.stage * kWStride, src, kRecordBytes, full + r.stage, pol_w);
+                    tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full + r.stage, pol_x);
+                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full + r.stage, pol_x);
+                } else {
+                    tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full + r.stage, pol_w);
+                    tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full + r.stage, pol_x);
                 }
-                mbar_wait(empty + r.stage, r.phase ^ 1);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(full + r.stage, kTxBytes);
-                    unsigned char* xs = s_x + r.stage * kXBytes;
-                    if constexpr (kAwq) {
-                        tma_bulk_g2s(s_w + r.stage * kWStride, src, kRecordBytes, full + r.stage, pol_w);
-                        tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full + r.stage, pol_x);
-                        tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full + r.stage, pol_x);
-                    } else {
-                        tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full + r.stage, pol_w);
-                        tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full + r.stage, pol_x);
+            }
+            __syncwarp();
+            src += kRecordStride;
+            r.advance(kStages);
+        }
+    } else if (warp <= 2) {
+        // ===================== MMA issuers: warp 1 takes even CTA-local units, warp 2 odd ones =====================
+        const int par = warp - 1;
+        const uint32_t d_base = tmem_base + par * kAccHalf * MPAD;   // this warp's accumulators
+        constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+        int st = par % kStages, ph = (par / kStages) & 1;            // smem ring position of unit `u`
+        int ts = par % kAStages, pa = 0;                              // tensor-memory A ring position
+        int u = par, seg = 0, seg_begin = 0, in_tile = in_tile0;
+        while (seg_begin < n_units) {
+            const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
+            mbar_wait(acc_empty, (seg & 1) ^ 1);
+            tc_fence_after();
+            bool first = true;
+            for (; u < seg_end; u += 2) {
+                const bool last = u + 2 >= seg_end;
+                if constexpr (kAwq) {
+                    mbar_wait(a_full + ts, pa);
+                }
+                mbar_wait(full + st, ph);
+                tc_fence_after();
+                const uint32_t xs = smem_u32(s_x + st * kXBytes);
+                const uint64_t bd0 = kDescHi | (uint64_t)((xs & 0x3FFFF) >> 4);
+                if constexpr (kAwq) {
+                    const uint32_t a_col = tmem_base + kACol0 + ts * 64;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (MPAD * 128) + (kk & 3) * 32) >> 4);
+                            umma_ts_f16(d_base + (kk % kAccHalf) * MPAD, a_col + kk * 8, bd, kIdesc,
+                                        (first && kk < kAccHalf) ? 0u : 1u);
+                        }
+                        umma_commit(done + st);
+                        if (last) umma_commit(acc_full);
+                    }
+                } else {
+                    const uint32_t ws = smem_u32(s_w + st * kWStride);
+                    const uint64_t ad0 = kDescHi | (uint64_t)((ws & 0x3FFFF) >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_ss_f16(d_base + (kk % kAccHalf) * MPAD, ad0 + kk * 2, bd0 + kk * 2, kIdesc,
+                                        (first && kk < kAccHalf) ? 0u : 1u);
+                        umma_commit(done + st);
+                        if (last) umma_commit(acc_full);
                     }
                 }
                 __syncwarp();
-                src += kRecordBytes;
-                r.advance(kStages);
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
-        {
-            Ring r, ra;
-            int seg = 0;
-            int u = 0;                                                  // CTA-local unit index
-            const int n_units = (int)(u_end - u_begin);
-            int in_tile = (int)u_begin % p.units_per_tile;              // position of the next unit inside its tile
-            constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
-            while (u < n_units) {
-                const int seg_len = min(n_units - u, p.units_per_tile - in_tile);
-                mbar_wait(acc_empty, (seg & 1) ^ 1);
-                tc_fence_after();
-                for (int j = 0; j < seg_len; ++j) {
-                    mbar_wait(full + r.stage, r.phase);
-                    const uint32_t xs = smem_u32(s_x + r.stage * kXBytes);
-                    const uint64_t bd0 = kDescHi | (uint64_t)((xs & 0x3FFFF) >> 4);
-                    if constexpr (kAwq) {
-                        mbar_wait(a_full + ra.stage, ra.phase);
-                        tc_fence_after();
-                        const uint32_t a_col = tmem_base + kTmemACol0 + ra.stage * 64;
-                        if (elect_one()) {
-#pragma unroll
-                            for (int kk = 0; kk < 8; ++kk) {
-                                const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (MPAD * 128) + (kk & 3) * 32) >> 4);
-                                umma_ts_f16(tmem_base + (kk % kNumAcc) * MPAD, a_col + kk * 8, bd, kIdesc,
-                                            (j == 0 && kk < kNumAcc) ? 0u : 1u);
-                            }
-                            umma_commit(a_empty + ra.stage);
-                            umma_commit(empty + r.stage);
-                            if (j == seg_len - 1) umma_commit(acc_full);
-                        }
-                        __syncwarp();
-                        ra.advance(kTmemAStages);
-                    } else {
-                        tc_fence_after();
-                        const uint32_t ws = smem_u32(s_w + r.stage * kWStride);
-                        const uint64_t ad0 = kDescHi | (uint64_t)((ws & 0x3FFFF) >> 4);
-                        if (elect_one()) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_ss_f16(tmem_base + (kk % kNumAccF16) * MPAD, ad0 + kk * 2, bd0 + kk * 2, kIdesc,
-                                            (j == 0 && kk < kNumAccF16) ? 0u : 1u);
-                            umma_commit(empty + r.stage);
-                            if (j == seg_len - 1) umma_commit(acc_full);
-                        }
-                        __syncwarp();
-                    }
-                    r.advance(kStages);
+                first = false;
+                st += 2;
+                while (st >= kStages) {
+                    st -= kStages;
+                    ph ^= 1;
                 }
-                u += seg_len;
-                in_tile = 0;
-                ++seg;
+                ts += 2;
+                if (ts >= kAStages) {
+                    ts -= kAStages;
+                    pa ^= 1;
+                }
             }
+            if (first) {                     // this warp had no unit in the segment: plain arrival
+                if (elect_one()) mbar_arrive(acc_full);
+                __syncwarp();
+            }
+            seg_begin = seg_end;
+            in_tile = 0;
+            ++seg;
         }
     } else {
         // ===================== dequant (AWQ) + epilogue warps =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may touch
-        const int grp = (warp - 2) >> 2;             // dequant group 0..kDqGroups-1; group 0 also runs the epilogue
+        const int grp = (warp - 3) >> 2;             // dequant group 0..kDqGroups-1; group 0 also runs the epilogue
         const bool is_epi = grp == 0;
         const int fl = q * 32 + lane;                // feature lane 0..127
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        int seg = 0;
-        long long u = u_begin;
+        int seg = 0, seg_begin = 0, in_tile = in_tile0, tile = tile0;
         int mine = grp;                              // CTA-local index of this group's next unit
-        int dq_st = grp % kStages, dq_ph = 0, dq_ts = grp % kTmemAStages, dq_pa = 0;   // its ring positions
-        while (u < u_end) {
-            const int tile = (int)u / p.units_per_tile;
-            const long long tile_u0 = (long long)tile * p.units_per_tile;
-            const long long seg_begin = u;
-            const long long seg_end = min(u_end, tile_u0 + p.units_per_tile);
+        int dq_st = grp % kStages, dq_ph = 0, dq_ts = grp % kAStages;      // ring positions of unit `mine`
+        int w_first = grp;                                                 // first unit of this group that re-uses a TMEM stage
+        while (w_first < kAStages) w_first += kDqGroups;
+        int w_st = (w_first - kAStages) % kStages, w_ph = 0;               // ring position of unit `mine - kAStages`
+        while (seg_begin < n_units) {
+            const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
             if constexpr (kAwq) {
-                const int seg_end_local = (int)(seg_end - u_begin);
-                for (; mine < seg_end_local; mine += kDqGroups) {
-                    const int st = dq_st, ph = dq_ph, ts = dq_ts, pa = dq_pa;
-                    dq_st += kDqGroups;                      // this group's next unit is kDqGroups further on
+                for (; mine < seg_end; mine += kDqGroups) {
+                    const int st = dq_st, ph = dq_ph, ts = dq_ts;
+                    dq_st += kDqGroups;
                     if (dq_st >= kStages) {
                         dq_st -= kStages;
                         dq_ph ^= 1;
                     }
                     dq_ts += kDqGroups;
-                    if (dq_ts >= kTmemAStages) {
-                        dq_ts -= kTmemAStages;
-                        dq_pa ^= 1;
-                    }
+                    if (dq_ts >= kAStages) dq_ts -= kAStages;
                     mbar_wait(full + st, ph);
                     const uint32_t rec = smem_u32(s_w + st * kWStride);
                     uint4 w4[4];
@@ -496,39 +513,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     const __half2 neg_co = as_h2((0xD400u | (z << 4)) * 0x10001u);      // -(64 + z) x2
                     const __half2 s2 = as_h2(sbits * 0x10001u);
                     const uint32_t magic = 0x64006400u;
-                    const uint32_t taddr = tmem_base + lane_addr + kTmemACol0 + ts * 64;
+                    const uint32_t taddr = tmem_base + lane_addr + kACol0 + ts * 64;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {                            // 4 chunks of 32 k (16 TMEM columns)
                         const uint32_t words[4] = {w4[c].x, w4[c].y, w4[c].z, w4[c].w};
                         uint32_t a[16];
 #pragma unroll
                         for (int w = 0; w < 4; ++w) dequant_word(words[w], magic, ce, neg_co, s2, &a[w * 4]);
-                        if (c == 0) {            // the MMA that last read this TMEM stage must have retired
-                            mbar_wait(a_empty + ts, pa ^ 1);
+                        if (c == 0 && mine >= kAStages) {
+                            // the unit that last used this tensor-memory stage (mine - kAStages) must have retired
+                            mbar_wait(done + w_st, w_ph);
                             tc_fence_after();
+                            w_st += kDqGroups;
+                            if (w_st >= kStages) {
+                                w_st -= kStages;
+                                w_ph ^= 1;
+                            }
                         }
                         UMB_TMEM_ST_X16(taddr + c * 16, a);
                     }
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(a_full + ts);
-                        mbar_arrive(empty + st);
-                    }
+                    if (lane == 0) mbar_arrive(a_full + ts);
                 }
             }
-            u = seg_end;
             if (is_epi) {
-                const bool whole = (seg_begin == tile_u0) && (seg_end == tile_u0 + p.units_per_tile);
+                const int seg_len = seg_end - seg_begin;
+                const bool whole = seg_len == p.units_per_tile;
+                // which MMA warps issued into their accumulators during this segment
+                const int n_odd = (seg_end >> 1) - (seg_begin >> 1);               // odd CTA-local indices in [begin, end)
+                const int use_mask = ((seg_len - n_odd) > 0 ? 1 : 0) | (n_odd > 0 ? 2 : 0);
                 mbar_wait(acc_full, seg & 1);
                 tc_fence_after();
                 if (whole) {
 #pragma unroll 1
                     for (int m0 = 0; m0 < MPAD; m0 += 16) {
                         float v[16];
-                        load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v);
-                        if (m0 + 16 >= MPAD) {       // accumulators fully read: hand TMEM back to the MMA warp
+                        load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v, use_mask);
+                        if (m0 + 16 >= MPAD) {       // accumulators fully read: hand TMEM back to the MMA warps
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(acc_empty);
@@ -541,7 +564,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
 #pragma unroll 1
                     for (int m0 = 0; m0 < MPAD; m0 += 16) {
                         float v[16];
-                        load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v);
+                        load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v, use_mask);
                         if (m0 + 16 >= MPAD) {
                             tc_fence_before();
                             __syncwarp();
@@ -554,9 +577,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     }
                     __threadfence();
                     named_bar_sync(1, 128);
+                    const long long tile_u0 = (long long)tile * p.units_per_tile;
                     const int c_first = sk_owner(tile_u0, U, P);
                     const int c_last = sk_owner(tile_u0 + p.units_per_tile - 1, U, P);
-                    if (warp == 2 && lane == 0) {
+                    if (warp == 3 && lane == 0) {
                         const int old = atomicAdd(p.counters + tile, 1);
                         const int last = (old == c_last - c_first) ? 1 : 0;
                         if (last) p.counters[tile] = 0;
@@ -585,6 +609,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     }
                 }
             }
+            seg_begin = seg_end;
+            in_tile = 0;
+            ++tile;
             ++seg;
         }
     }
@@ -678,7 +705,7 @@ awq_gemm_simt_kernel(const unsigned char* __restrict__ packed, const __half* __r
     for (int m0 = 0; m0 < M; m0 += 8) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int g = 0; g < G; ++g) {
-            const unsigned char* rec = packed + ((int64_t)tile * G + g) * kRecordBytes;
+            const unsigned char* rec = packed + ((int64_t)tile * G + g) * kRecordStride;
             const uint32_t zw = *reinterpret_cast<const uint32_t*>(rec + kRecZeroOff + (r >> 3) * 4);
             const int z = (int)((zw >> (4 * (r & 7))) & 0xFu);
             const __half s = *reinterpret_cast<const __half*>(rec + kRecScaleOff + r * 2);
@@ -745,6 +772,12 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, GemmParams 
             env_stages = e ? atoi(e) : 0;
         }
         if (env_stages > 0 && env_stages <= 16 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024) p.stages = env_stages;
+        static int env_pf = -1;
+        if (env_pf < 0) {
+            const char* e = getenv("UMB_GEMM_PREFETCH");
+            env_pf = e ? atoi(e) : 0;
+        }
+        p.prefetch = env_pf;
     }
     const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages);
     static int attr_smem = 0;
@@ -823,7 +856,7 @@ using namespace umb;
 
 extern "C" size_t umb_awq_packed_bytes(int K, int N_total, int group) {
     if (group != kGroup || K <= 0 || N_total <= 0 || (K % kGroup) != 0) return 0;
-    return (size_t)((N_total + kTileN - 1) / kTileN) * (K / kGroup) * kRecordBytes;
+    return (size_t)((N_total + kTileN - 1) / kTileN) * (K / kGroup) * kRecordStride;
 }
 
 extern "C" size_t umb_gemm_workspace_bytes(int M, int K, int N_total) {
