@@ -115,12 +115,15 @@ enum {
 typedef struct {
     int mask_mode;
     int prefix_len;                /* committed prefix n (modes 0, 2)                              */
-    const int32_t* dyn;            /* optional device int32[2] = {prefix_len, kv_len}; overrides the
-                                      host values (CUDA-graph replay with a moving prefix)          */
+    const int32_t* dyn;            /* optional device int32* n (the committed prefix length, e.g. the
+                                      state word umb_tree_accept maintains): prefix_len and kv_len
+                                      are then OFFSETS added to n[0] at run time, so one captured
+                                      CUDA graph serves a moving prefix                             */
     const uint32_t* tree_bits;     /* [qo, tree_words]                                             */
     int tree_words;
     const uint8_t* dense_mask;
     int64_t mask_stride;
+    int kv_len_bound;              /* with dyn: upper bound of the run-time kv_len (grid sizing)   */
 } umb_attn_mask_t;
 
 size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int head_dim, int max_kv_len);
@@ -151,8 +154,9 @@ int umb_rope_append_f16(const void* qkv, int64_t ld_qkv, void* q_out, void* k_ca
  *      state[0] if state != NULL), eos int64[n_eos].
  * Out: tokens[n : n+len+1], position_ids updated exactly as the reference's verify() does;
  *      result int32[4 + N]: {accept_len, continue, new_num_nodes, bonus_lo32, path_abs[0..len)}
- *      (device or mapped-pinned memory); state[0] = new_num_nodes, state[1] = new_num_nodes + N
- *      if state != NULL. */
+ *      (device or mapped-pinned memory); if state != NULL (device int32[4]): state[0] = new_num_nodes,
+ *      state[1] = new_num_nodes + N, state[2] = the num_nodes this call started from (the gather
+ *      offset: pass &state[2] as umb_kv_gather's offset_dev). */
 int umb_tree_accept(const int64_t* sampled, int64_t* tokens, int64_t* position_ids, const int32_t* parents,
                     const int32_t* depth, int N, int num_nodes, int32_t* state, const int64_t* eos, int n_eos,
                     int32_t* result, umb_stream_t stream);
@@ -242,6 +246,21 @@ size_t umb_llama_gemm_ws_bytes(int hidden, int intermediate, int num_q_heads, in
 int umb_llama_forward(const umb_llama_t* model, const int64_t* input_ids, const int64_t* position_ids, int rows,
                       int kv_offset, const umb_attn_mask_t* mask, float* logits, int logits_from_row,
                       unsigned long long* argmax_keys, umb_stream_t stream);
+
+/* Graph-replay form of the tree forward: every position-dependent quantity is read on the device
+ * from n_dev[0] (the committed prefix length n, maintained by umb_tree_accept through `state`):
+ * the rows are tokens_base[n + row_offset + r] / position_base[n + row_offset + r], they are
+ * appended at cache rows n + row_offset + r, and row r sees [0, n) plus the set bits of
+ * tree_bits[r, :] (offset n).  kv_len_bound >= n + row_offset + rows sizes the attention grid.
+ * rows <= 128.  One captured CUDA graph of this call is valid until n exceeds the bound. */
+int umb_llama_forward_dyn(const umb_llama_t* model, const int64_t* tokens_base, const int64_t* position_base,
+                          int rows, const int32_t* n_dev, int row_offset, int kv_len_bound,
+                          const uint32_t* tree_bits, int tree_words, float* logits, unsigned long long* argmax_keys,
+                          umb_stream_t stream);
+
+/* tokens_base[n_dev[0] + offset + i] = src[i], i < count  (draft tokens of the next tree level) */
+int umb_store_tokens(int64_t* tokens_base, const int32_t* n_dev, int offset, const int64_t* src, int count,
+                     umb_stream_t stream);
 
 #ifdef __cplusplus
 }

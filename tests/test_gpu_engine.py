@@ -24,10 +24,11 @@ DRAFT = ollama.LlamaShape(hidden_size=256, intermediate_size=512, num_hidden_lay
                           rope_theta=10000.0)
 
 
-def _engine(tree="sequoia_tree-3x4.json", S=384, draft_same=False):
+def _engine(tree="sequoia_tree-3x4.json", S=384, draft_same=False, graph=True):
     from umbrella_b200.models.llama import SyntheticLlama
     from umbrella_b200.speculation.static_speculation_engine import StaticSpeculationEngine
-    eng = StaticSpeculationEngine("draft", "target", device=DEV, growmap_path=tree, max_length=S, safe_buffer=48)
+    eng = StaticSpeculationEngine("draft", "target", device=DEV, growmap_path=tree, max_length=S, safe_buffer=48,
+                                  graph_iteration=graph, graph_bucket=128)
     target = SyntheticLlama(TARGET, max_length=S, awq=True, seed=21, device=DEV)
     draft = SyntheticLlama(TARGET, max_length=S, awq=True, seed=21, device=DEV) if draft_same else \
         SyntheticLlama(DRAFT, max_length=S, awq=False, seed=22, device=DEV)
@@ -54,9 +55,12 @@ def _ar_greedy(model, prompt, n_new):
     return out
 
 
-@pytest.mark.parametrize("tree,draft_same", [("sequoia_tree-3x4.json", False), ("8b_sequoia_tree-5x6.json", True)])
-def test_greedy_speculation_is_lossless(tree, draft_same):
-    eng = _engine(tree, draft_same=draft_same)
+@pytest.mark.parametrize("tree,draft_same,graph", [("sequoia_tree-3x4.json", False, False),
+                                                   ("sequoia_tree-3x4.json", False, True),
+                                                   ("8b_sequoia_tree-5x6.json", True, True)])
+def test_greedy_speculation_is_lossless(tree, draft_same, graph):
+    """graph=True runs every iteration as one captured CUDA graph (several buckets of 128 positions)."""
+    eng = _engine(tree, draft_same=draft_same, graph=graph)
     g = torch.Generator().manual_seed(3)
     prompt = torch.randint(3, TARGET.vocab_size, (40,), generator=g)
     n_new = 48
@@ -81,7 +85,7 @@ def test_greedy_speculation_is_lossless(tree, draft_same):
 def test_scripted_acceptance_matches_oracle_bookkeeping():
     """Scripted run: accept lengths / tokens / positions follow the oracle's verify_step exactly."""
     from umbrella_b200.speculation.scripted import ScriptedAcceptance
-    eng = _engine()
+    eng = _engine(graph=False)          # step-wise inspection needs the eager build_tree / verify split
     gm = eng.growmap
     succ = gm["Successors"]
     parents = otree.successors_to_parents(succ)
@@ -113,3 +117,19 @@ def test_scripted_acceptance_matches_oracle_bookkeeping():
         assert eng.target_model.kv_cache.kv_offset == eng.num_nodes == eng.draft_model.kv_cache.kv_offset
         total += alen
     assert total / 12 > 1.5      # DEFAULT_ACC on the 3x4 tree: ~3.4 expected
+
+
+def test_graph_iteration_equals_eager_under_script():
+    """Same scripted acceptance through the captured-graph iteration and the eager path: identical
+    tokens, accept lengths and step counts."""
+    from umbrella_b200.speculation.scripted import ScriptedAcceptance
+    outs = []
+    g = torch.Generator().manual_seed(4)
+    prompt = torch.randint(3, TARGET.vocab_size, (70,), generator=g).tolist()
+    for graph in (False, True):
+        eng = _engine(graph=graph)
+        eng.acceptance_script = ScriptedAcceptance(eng.Successors, seed=8, max_iters=256, device=DEV)
+        outs.append(eng.generate(input_ids=prompt, max_new_tokens=160))
+    assert outs[0]["generated_tokens"] == outs[1]["generated_tokens"]
+    assert outs[0]["large_model_steps"] == outs[1]["large_model_steps"]
+    assert outs[0]["avg_accept_tokens"] > 2.5

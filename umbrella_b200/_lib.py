@@ -25,7 +25,7 @@ class Epilogue(C.Structure):
 
 class AttnMask(C.Structure):
     _fields_ = [("mask_mode", c_int), ("prefix_len", c_int), ("dyn", c_void_p), ("tree_bits", c_void_p),
-                ("tree_words", c_int), ("dense_mask", c_void_p), ("mask_stride", c_int64)]
+                ("tree_words", c_int), ("dense_mask", c_void_p), ("mask_stride", c_int64), ("kv_len_bound", c_int)]
 
 
 class LlamaLayer(C.Structure):
@@ -78,6 +78,9 @@ SIGNATURES = {
     "umb_llama_gemm_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "umb_llama_forward": (c_int, [C.POINTER(LlamaModel), c_void_p, c_void_p, c_int, c_int, C.POINTER(AttnMask),
                                   c_void_p, c_int, c_void_p, c_void_p]),
+    "umb_llama_forward_dyn": (c_int, [C.POINTER(LlamaModel), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                      c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "umb_store_tokens": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

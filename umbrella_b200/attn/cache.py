@@ -49,11 +49,11 @@ class KV_Cache:
             buf[4:4 + m] = indices.to(device=self.device, dtype=torch.int32)
         self.gather_from_result(buf, offset, m)
 
-    def gather_from_result(self, result: torch.Tensor, offset: int, accept_len: int):
+    def gather_from_result(self, result: torch.Tensor, offset: int, accept_len: int, offset_dev=None):
         """Fast path: ``result`` is the device buffer written by umb_tree_accept (no host round trip
-        for the path itself)."""
+        for the path itself); ``offset_dev`` (device int32) overrides ``offset`` for graph replay."""
         ops.kv_gather(self.k_cache, self.v_cache, result, offset, "LSHD",
-                      zero_upto=self.max_length if self.zero_tail else 0)
+                      zero_upto=self.max_length if self.zero_tail else 0, offset_dev=offset_dev)
         self.kv_offset = offset + accept_len
 
     # cache.py:53-65 -- append at kv_offset; the values of storage_ids are ignored, only their count

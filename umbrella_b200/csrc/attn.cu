@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParam
     const int g4 = lane >> 2, t4 = lane & 3;
     const int hkv = blockIdx.y, split = blockIdx.z;
     const int rows_total = p.qo * p.G;
-    const int prefix_len = p.dyn ? p.dyn[0] : p.prefix_len;
-    const int kv_len = p.dyn ? p.dyn[1] : p.kv_len;
+    const int prefix_len = p.dyn ? p.dyn[0] + p.prefix_len : p.prefix_len;
+    const int kv_len = p.dyn ? p.dyn[0] + p.kv_len : p.kv_len;
 
     const int row_base = blockIdx.x * kBM + warp * 16;
     // the two rows this thread owns inside its warp's 16-row slab
@@ -389,8 +389,8 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const Attn
     const int g4 = lane >> 2, t4 = lane & 3;
     const int hkv = blockIdx.y, split = blockIdx.z;
     const int rows_total = p.qo * p.G;
-    const int prefix_len = p.dyn ? p.dyn[0] : p.prefix_len;
-    const int kv_len = p.dyn ? p.dyn[1] : p.kv_len;
+    const int prefix_len = p.dyn ? p.dyn[0] + p.prefix_len : p.prefix_len;
+    const int kv_len = p.dyn ? p.dyn[0] + p.kv_len : p.kv_len;
     // per-warp ring: [2 stages][K | V][kSBN][D]
     __half* ring = reinterpret_cast<__half*>(smem_raw) + warp * (4 * kSBN * D);
 
@@ -679,13 +679,14 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
                                  void* workspace, size_t workspace_bytes, umb_stream_t stream) {
     UMB_CHECK_ARG(q && k_cache && v_cache && out && mask);
     UMB_CHECK_ARG(qo >= 1 && kv_len >= 1 && num_q_heads >= 1 && num_kv_heads >= 1);
+    const int kv_bound = mask->dyn ? (mask->kv_len_bound > kv_len ? mask->kv_len_bound : kv_len) : kv_len;
     UMB_CHECK_ARG(num_q_heads % num_kv_heads == 0);
     UMB_CHECK_ARG((kv_tok_stride % 8) == 0 && (kv_head_stride % 8) == 0);
     UMB_CHECK_ARG((((uintptr_t)q | (uintptr_t)k_cache | (uintptr_t)v_cache | (uintptr_t)out) & 15) == 0);
     if (head_dim != 64 && head_dim != 128) return UMB_ERR_UNSUPPORTED;
     UMB_CHECK_ARG(mask->mask_mode >= 0 && mask->mask_mode <= 2);
     if (mask->mask_mode == UMB_MASK_TREE) UMB_CHECK_ARG(mask->tree_bits && mask->tree_words >= 1);
-    if (mask->mask_mode == UMB_MASK_DENSE) UMB_CHECK_ARG(mask->dense_mask && mask->mask_stride >= kv_len);
+    if (mask->mask_mode == UMB_MASK_DENSE) UMB_CHECK_ARG(mask->dense_mask && mask->mask_stride >= kv_len && !mask->dyn);
 
     AttnParams p{};
     p.q = (const __half*)q;
@@ -714,9 +715,9 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
     // while that re-read is cheap; long contexts with many slabs go to the 64-row tile kernel.
     const int rows_total = qo * p.G;
     const int slabs = (rows_total + 15) / 16;
-    const bool slab = !(kv_len > 8192 && slabs > 2);
+    const bool slab = !(kv_bound > 8192 && slabs > 2);
     const int ctas_base = (slab ? slabs : (rows_total + kBM - 1) / kBM) * p.Hkv;
-    const int kv_tiles = (kv_len + (slab ? kSBN : kBN) - 1) / (slab ? kSBN : kBN);
+    const int kv_tiles = (kv_bound + (slab ? kSBN : kBN) - 1) / (slab ? kSBN : kBN);
     const int tiles_per_cta_min = slab ? 32 : 4;              // slab CTAs run 4 tiles at a time (one per warp)
     int splits = (kv_tiles + tiles_per_cta_min - 1) / tiles_per_cta_min;
     const int by_ctas = (2 * sm_count()) / (ctas_base > 0 ? ctas_base : 1);

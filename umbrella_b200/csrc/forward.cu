@@ -16,22 +16,31 @@ static int linear(const umb_llama_t* m, const void* x, int64_t ldx, const void* 
 
 #define UMB_TRY(expr) do { int rc__ = (expr); if (rc__ != UMB_OK) return rc__; } while (0)
 
+// n_dev == NULL: ids / pos point at the rows, kv_offset is the append position (host value).
+// n_dev != NULL: ids / pos are base pointers, kv_offset is the row offset added to n_dev[0] on the device.
 static int forward_chunk(const umb_llama_t* m, const int64_t* ids, const int64_t* pos, int rows, int kv_offset,
                          const umb_attn_mask_t* mask, float* logits, int logits_from, unsigned long long* keys,
-                         umb_stream_t st) {
+                         umb_stream_t st, const int32_t* n_dev = nullptr) {
     const int H = m->hidden_size, I = m->intermediate_size, Hq = m->num_q_heads, Hkv = m->num_kv_heads, D = m->head_dim;
     const int qkv_n = (Hq + 2 * Hkv) * D;
     const int64_t tok_stride = (int64_t)Hkv * D;
     const int64_t layer_elems = (int64_t)m->max_length * tok_stride;
-    UMB_TRY(umb_embedding_f16(ids, m->embed, m->hidden, rows, H, st));
+    if (n_dev)
+        UMB_TRY(embedding_dyn(ids, n_dev, kv_offset, m->embed, m->hidden, rows, H, (cudaStream_t)st));
+    else
+        UMB_TRY(umb_embedding_f16(ids, m->embed, m->hidden, rows, H, st));
     for (int l = 0; l < m->num_layers; ++l) {
         const umb_llama_layer_t& L = m->layers[l];
         __half* kc = (__half*)m->k_cache + l * layer_elems;
         __half* vc = (__half*)m->v_cache + l * layer_elems;
         UMB_TRY(umb_rmsnorm_f16(m->hidden, L.input_norm, m->normed, rows, H, m->rms_eps, st));
         UMB_TRY(linear(m, m->normed, H, L.wqkv, m->qkv, qkv_n, rows, H, qkv_n, nullptr, st));
-        UMB_TRY(umb_rope_append_f16(m->qkv, qkv_n, m->q_rot, kc, vc, m->cos, m->sin, pos, rows, Hq, Hkv, D, tok_stride,
-                                    D, kv_offset, nullptr, st));
+        if (n_dev)
+            UMB_TRY(rope_append_dyn(m->qkv, qkv_n, m->q_rot, kc, vc, m->cos, m->sin, pos, n_dev, kv_offset, rows, Hq, Hkv,
+                                    D, tok_stride, D, (cudaStream_t)st));
+        else
+            UMB_TRY(umb_rope_append_f16(m->qkv, qkv_n, m->q_rot, kc, vc, m->cos, m->sin, pos, rows, Hq, Hkv, D,
+                                        tok_stride, D, kv_offset, nullptr, st));
         UMB_TRY(umb_tree_attn_f16(m->q_rot, kc, vc, m->attn_out, rows, kv_offset + rows, Hq, Hkv, D, tok_stride, D,
                                   mask, 0.f, 0.f, m->attn_ws, m->attn_ws_bytes, st));
         umb_epilogue_t res{};
@@ -110,4 +119,23 @@ extern "C" int umb_llama_forward(const umb_llama_t* m, const int64_t* input_ids,
         if (rc != UMB_OK) return rc;
     }
     return UMB_OK;
+}
+
+extern "C" int umb_llama_forward_dyn(const umb_llama_t* m, const int64_t* tokens_base, const int64_t* position_base,
+                                     int rows, const int32_t* n_dev, int row_offset, int kv_len_bound,
+                                     const uint32_t* tree_bits, int tree_words, float* logits,
+                                     unsigned long long* argmax_keys, umb_stream_t stream) {
+    UMB_CHECK_ARG(m && tokens_base && position_base && n_dev && tree_bits && rows >= 1 && rows <= 128);
+    UMB_CHECK_ARG(row_offset >= 0 && tree_words >= 1 && kv_len_bound >= row_offset + rows && kv_len_bound <= m->max_length);
+    UMB_CHECK_ARG(m->layers && m->embed && m->final_norm && m->cos && m->sin && m->k_cache && m->v_cache);
+    UMB_CHECK_ARG(m->hidden && m->normed && m->qkv && m->q_rot && m->attn_out && m->act && m->gemm_ws);
+    UMB_CHECK_ARG(!argmax_keys || logits);
+    umb_attn_mask_t mk{};
+    mk.mask_mode = UMB_MASK_TREE;
+    mk.prefix_len = 0;                 // offsets relative to n_dev[0]
+    mk.dyn = n_dev;
+    mk.tree_bits = tree_bits;
+    mk.tree_words = tree_words;
+    mk.kv_len_bound = kv_len_bound;
+    return umb::forward_chunk(m, tokens_base, position_base, rows, row_offset, &mk, logits, 0, argmax_keys, stream, n_dev);
 }

@@ -92,8 +92,9 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
 
 // ids may live at a device-resident offset (CUDA-graph replay with a moving window)
 __global__ void embedding_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ ids_offset_dev,
-                                 const __half* __restrict__ table, __half* __restrict__ y, int hidden) {
-    const int64_t off = ids_offset_dev ? ids_offset_dev[0] : 0;
+                                 int ids_offset_add, const __half* __restrict__ table, __half* __restrict__ y,
+                                 int hidden) {
+    const int64_t off = ids_offset_dev ? (int64_t)ids_offset_dev[0] + ids_offset_add : 0;
     const int64_t id = ids[off + blockIdx.x];
     const uint4* src = reinterpret_cast<const uint4*>(table + id * hidden);
     uint4* dst = reinterpret_cast<uint4*>(y + (int64_t)blockIdx.x * hidden);
@@ -110,16 +111,17 @@ __global__ void rope_append_kernel(const __half* __restrict__ qkv, int64_t ld_qk
                                    const int64_t* __restrict__ position_ids, const int32_t* __restrict__ pos_offset_dev,
                                    int Hq, int Hkv, int D, int64_t kv_tok_stride, int64_t kv_head_stride,
                                    int kv_offset_host, const int32_t* __restrict__ kv_offset_dev) {
+    // with the device words: kv row / position index = dev[0] + host offset
     const int t = blockIdx.x, h = blockIdx.y, d = threadIdx.x, half_d = D >> 1;
     const __half* src = qkv + (int64_t)t * ld_qkv + (int64_t)h * D;
-    const int kv_offset = kv_offset_dev ? kv_offset_dev[0] : kv_offset_host;
+    const int kv_offset = kv_offset_dev ? kv_offset_dev[0] + kv_offset_host : kv_offset_host;
     if (h >= Hq + Hkv) {  // V: plain copy
         __half* dst = v_cache + (int64_t)(kv_offset + t) * kv_tok_stride + (int64_t)(h - Hq - Hkv) * kv_head_stride;
         dst[d] = src[d];
         dst[d + half_d] = src[d + half_d];
         return;
     }
-    const int64_t pos = position_ids[(pos_offset_dev ? pos_offset_dev[0] : 0) + t];
+    const int64_t pos = position_ids[(pos_offset_dev ? pos_offset_dev[0] + kv_offset_host : 0) + t];
     const __half c0 = cos_t[pos * D + d], c1 = cos_t[pos * D + d + half_d];
     const __half s0 = sin_t[pos * D + d], s1 = sin_t[pos * D + d + half_d];
     const __half x0 = src[d], x1 = src[d + half_d];
@@ -217,11 +219,32 @@ extern "C" int umb_embedding_f16(const int64_t* ids, const void* table, void* y,
                                  umb_stream_t stream) {
     UMB_CHECK_ARG(ids && table && y && rows >= 1 && hidden >= 8 && (hidden % 8) == 0);
     UMB_CHECK_ARG((((uintptr_t)table | (uintptr_t)y) & 15) == 0);
-    embedding_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(ids, nullptr, (const __half*)table, (__half*)y, hidden);
+    embedding_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(ids, nullptr, 0, (const __half*)table, (__half*)y, hidden);
     count_launches(1);
     UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
+
+namespace umb {
+int embedding_dyn(const int64_t* ids_base, const int32_t* n_dev, int offset, const void* table, void* y, int rows,
+                  int hidden, cudaStream_t st) {
+    embedding_kernel<<<rows, 256, 0, st>>>(ids_base, n_dev, offset, (const __half*)table, (__half*)y, hidden);
+    count_launches(1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
+// position_ids is the BASE pointer; rows are read at n_dev[0] + offset + t and appended at the same cache rows
+int rope_append_dyn(const void* qkv, int64_t ld_qkv, void* q_out, void* k_cache, void* v_cache, const void* cos,
+                    const void* sin, const int64_t* position_base, const int32_t* n_dev, int offset, int qo, int Hq,
+                    int Hkv, int D, int64_t kv_tok_stride, int64_t kv_head_stride, cudaStream_t st) {
+    rope_append_kernel<<<dim3(qo, Hq + 2 * Hkv), D / 2, 0, st>>>(
+        (const __half*)qkv, ld_qkv, (__half*)q_out, (__half*)k_cache, (__half*)v_cache, (const __half*)cos,
+        (const __half*)sin, position_base, n_dev, Hq, Hkv, D, kv_tok_stride, kv_head_stride, offset, n_dev);
+    count_launches(1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
+}  // namespace umb
 
 extern "C" int umb_rope_append_f16(const void* qkv, int64_t ld_qkv, void* q_out, void* k_cache, void* v_cache,
                                    const void* cos, const void* sin, const int64_t* position_ids, int qo,

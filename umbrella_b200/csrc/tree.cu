@@ -105,6 +105,7 @@ tree_accept_kernel(const int64_t* __restrict__ sampled, int64_t* __restrict__ to
         if (state) {
             state[0] = new_n;
             state[1] = new_n + N;
+            state[2] = n;
         }
     }
     if (i < alen) result[4 + i] = n + s_path[i];
@@ -166,6 +167,23 @@ extern "C" int umb_kv_gather(void* k_cache, void* v_cache, int num_planes, int64
     umb::kv_gather_kernel<<<dim3(num_planes, 2), threads, 0, (cudaStream_t)stream>>>(
         (unsigned char*)k_cache, (unsigned char*)v_cache, plane_stride_bytes, row_stride_bytes, row_bytes, result,
         offset, offset_dev, zero_upto);
+    umb::count_launches(1);
+    UMB_LAUNCH_CHECK();
+    return UMB_OK;
+}
+
+namespace umb {
+__global__ void store_tokens_kernel(int64_t* __restrict__ tokens, const int32_t* __restrict__ n_dev, int offset,
+                                    const int64_t* __restrict__ src, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) tokens[(int64_t)n_dev[0] + offset + i] = src[i];
+}
+}  // namespace umb
+
+extern "C" int umb_store_tokens(int64_t* tokens_base, const int32_t* n_dev, int offset, const int64_t* src, int count,
+                                umb_stream_t stream) {
+    UMB_CHECK_ARG(tokens_base && n_dev && src && count >= 1 && offset >= 0);
+    umb::store_tokens_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(tokens_base, n_dev, offset, src, count);
     umb::count_launches(1);
     UMB_LAUNCH_CHECK();
     return UMB_OK;

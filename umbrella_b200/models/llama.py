@@ -278,6 +278,22 @@ class Llama:
         m = ops.make_mask(ops.UMB_MASK_TREE, prefix_len=prefix_len, tree_bits=tree_bits)
         return self._forward(input_ids, position_ids, m, argmax_keys=argmax_keys, want_logits=want_logits)
 
+    @torch.inference_mode()
+    def forward_dyn(self, tokens_base: torch.Tensor, position_base: torch.Tensor, rows: int, n_dev: torch.Tensor,
+                    row_offset: int, kv_len_bound: int, tree_bits: torch.Tensor, logits: torch.Tensor | None = None,
+                    argmax_keys: torch.Tensor | None = None):
+        """Graph-replay form of verify_forward: the committed prefix length is read on the device from
+        ``n_dev`` (int32), so a captured CUDA graph of this call follows the moving prefix.  Host-side
+        ``kv_offset`` bookkeeping is the caller's job."""
+        assert tokens_base.dtype == torch.int64 and position_base.dtype == torch.int64 and n_dev.dtype == torch.int32
+        _lib.check(_lib.load().umb_llama_forward_dyn(
+            C.byref(self._model_struct()), C.c_void_p(tokens_base.data_ptr()), C.c_void_p(position_base.data_ptr()), rows,
+            C.c_void_p(n_dev.data_ptr()), row_offset, kv_len_bound, C.c_void_p(tree_bits.data_ptr()), tree_bits.shape[1],
+            C.c_void_p(logits.data_ptr()) if logits is not None else None,
+            C.c_void_p(argmax_keys.data_ptr()) if argmax_keys is not None else None,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "llama_forward_dyn")
+        return logits
+
     # ------------------------------------------------------------------ cache ops (llama.py:136-142)
     def gather_kv_incremental(self, indices, offset: int):
         self.kv_cache.gather_kv_incremental(indices, offset)

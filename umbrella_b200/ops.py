@@ -211,8 +211,14 @@ def tree_accept(sampled, tokens, position_ids, parents, depth, num_nodes: int, e
           "tree_accept")
 
 
+def store_tokens(tokens: torch.Tensor, n_dev: torch.Tensor, offset: int, src: torch.Tensor):
+    """tokens[n_dev[0] + offset + i] = src[i] with n read on the device (graph replay)."""
+    _cuda(tokens, torch.int64, "tokens"), _cuda(src, torch.int64, "src"), _cuda(n_dev, torch.int32, "n_dev")
+    check(_lib.load().umb_store_tokens(_p(tokens), _p(n_dev), offset, _p(src), src.numel(), _stream()), "store_tokens")
+
+
 def kv_gather(k_cache: torch.Tensor, v_cache: torch.Tensor, result: torch.Tensor, offset: int, layout: str = "LSHD",
-              zero_upto: int = 0):
+              zero_upto: int = 0, offset_dev: torch.Tensor | None = None):
     """In-place compaction of accepted rows for every layer.  k/v: [L, S, Hkv, D] ("LSHD", KV_Cache)
     or [L, Hkv, S, D] ("LHSD", StaticKV_Cache)."""
     es = k_cache.element_size()
@@ -223,7 +229,8 @@ def kv_gather(k_cache: torch.Tensor, v_cache: torch.Tensor, result: torch.Tensor
         L, Hkv, S, D = k_cache.shape
         planes, plane_stride, row_stride, row_bytes = L * Hkv, k_cache.stride(1) * es, k_cache.stride(2) * es, D * es
     check(_lib.load().umb_kv_gather(_p(k_cache), _p(v_cache), planes, plane_stride, row_stride, row_bytes, _p(result),
-                                    offset, None, zero_upto, _stream()), "kv_gather")
+                                    offset, _p(offset_dev) if offset_dev is not None else None, zero_upto, _stream()),
+          "kv_gather")
 
 
 # ---------------------------------------------------------------------------------------------

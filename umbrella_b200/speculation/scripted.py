@@ -35,9 +35,26 @@ class ScriptedAcceptance:
         self.choice = torch.from_numpy(choice).to(device)
         self.it = 0
         self.max_iters = max_iters
+        self.it_dev = torch.zeros(1, dtype=torch.int64, device=device)     # iteration counter for graph replay
 
     def reset(self):
         self.it = 0
+        self.it_dev.zero_()
+
+    def snapshot(self):
+        return int(self.it_dev.item())
+
+    def restore(self, it: int):
+        self.it_dev.fill_(it)
+
+    def graph_call(self, engine, sampled: torch.Tensor, state: torch.Tensor) -> torch.Tensor:
+        """Capturable form: the iteration counter and the prefix length live on the device."""
+        row = self.choice.index_select(0, self.it_dev % self.max_iters)[0]
+        self.it_dev += 1
+        idx = state[0:1].to(torch.int64) + row.clamp(min=0)
+        picked = engine.tokens[0].gather(0, idx)
+        self.last = torch.where(row >= 0, picked, sampled)
+        return self.last
 
     def __call__(self, engine, sampled: torch.Tensor) -> torch.Tensor:
         row = self.choice[self.it % self.max_iters]

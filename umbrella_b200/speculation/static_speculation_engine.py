@@ -44,6 +44,11 @@ class StaticSpeculationEngine(BaseEngine):
         self.topk = kwargs.pop("topk", 32)
         self.config = kwargs
         self.acceptance_script = None      # benchmark hook: callable(engine, sampled) -> sampled
+        # One CUDA graph per speculative-decoding iteration (all draft levels + verify + accept + gathers):
+        # the reference graphs only the draft forward (llama.py:505-533); here the whole iteration is one
+        # launch and the host reads back 3 ints.  Greedy decoding only; other settings run eagerly.
+        self.graph_iteration = kwargs.pop("graph_iteration", True)
+        self.graph_bucket = kwargs.pop("graph_bucket", 512)
         self.draft_model = None
         self.target_model = None
         self.stats = {"verify_calls": 0}
@@ -107,10 +112,24 @@ class StaticSpeculationEngine(BaseEngine):
         self._result_host = torch.zeros(4 + N, dtype=torch.int32).pin_memory()
         self._set_eos(self.eos_tokens)
         self.uniform_samples = torch.rand(3, N, device=dev)
+        # device-resident iteration state for graph replay: [n, n + N, n before the last accept, spare]
+        self._state = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._graphs = {}
+        self._tree_pending = False
+        V = self.vocab_size
+        self._draft_logits = [torch.empty((b - a, self.draft_model.config.vocab_size), dtype=torch.float32, device=dev)
+                              for (a, b) in self.level_ranges[:-1]]
+        self._target_logits = torch.empty((N, V), dtype=torch.float32, device=dev)
 
     def _set_eos(self, eos_tokens):
         self.eos_tokens = list(eos_tokens)
         self._eos_dev = torch.tensor(self.eos_tokens, dtype=torch.int64, device=self.device) if self.eos_tokens else None
+        self._graphs = {}                  # captured graphs hold the old pointer
+
+    def _sync_state(self):
+        """Push the host's num_nodes to the device state word (after prefill / append / reset)."""
+        self._state[:3] = torch.tensor([self.num_nodes, self.num_nodes + self.tree_size, self.num_nodes],
+                                       dtype=torch.int32)
 
     # ------------------------------------------------------------------ prefill / append (static...:133-209)
     def _encode(self, text):
@@ -139,6 +158,7 @@ class StaticSpeculationEngine(BaseEngine):
         self.draft_model.prefill_forward(ids, pos, want_logits=False)
         logits = self.target_model.prefill_forward(ids, pos, last_only=True)
         self.tokens[0, self.num_nodes] = ops.argmax(logits)[0]
+        self._sync_state()
         return True
 
     @torch.inference_mode()
@@ -157,13 +177,73 @@ class StaticSpeculationEngine(BaseEngine):
         self.draft_model.prefill_forward(ids, pos, want_logits=False)
         logits = self.target_model.prefill_forward(ids, pos, last_only=True)
         self.tokens[0, self.num_nodes] = ops.argmax(logits)[0]
+        self._sync_state()
         return True
 
     # ------------------------------------------------------------------ the loop
+    def _graph_ok(self) -> bool:
+        return bool(self.graph_iteration) and self.temperature < 0.05 and not (self.repetition_penalty > 1.01)
+
+    def _iteration_body(self, bound: int):
+        """Enqueue one whole iteration with every position read from the device state word."""
+        N = self.tree_size
+        tok, pos, st = self.tokens[0], self.position_ids[0], self._state
+        for step in range(self.tree_depth):
+            a, b = self.level_ranges[step]
+            last = step == self.tree_depth - 1
+            lg = None if last else self._draft_logits[step]
+            self.draft_model.forward_dyn(tok, pos, b - a, st, a, bound, self.tree_bits[a:b], logits=lg)
+            if not last:
+                width = max(self.branch_lists[step])
+                new_tokens = lg.topk(k=width).indices.flatten().index_select(0, self.sample_gather_indices[step])
+                ops.store_tokens(tok, st, b, new_tokens)
+        self.target_model.forward_dyn(tok, pos, N, st, 0, bound, self.tree_bits, logits=self._target_logits,
+                                      argmax_keys=self._argmax_keys)
+        sampled = ops.argmax_keys_to_ids(self._argmax_keys[:N])
+        if self.acceptance_script is not None:
+            sampled = self.acceptance_script.graph_call(self, sampled, st)
+        ops.tree_accept(sampled, tok, pos, self.parents, self.depth, 0, self._eos_dev, self._result, state=st)
+        self.draft_model.kv_cache.gather_from_result(self._result, 0, 0, offset_dev=st[2:3])
+        self.target_model.kv_cache.gather_from_result(self._result, 0, 0, offset_dev=st[2:3])
+        self._result_host.copy_(self._result, non_blocking=True)
+
+    def _run_iteration_graph(self):
+        n, N = self.num_nodes, self.tree_size
+        bucket = self.graph_bucket
+        bound = min(self.max_length, ((n + N) // bucket + 1) * bucket)
+        key = (bound, id(self.acceptance_script))
+        g = self._graphs.get(key)
+        if g is None:
+            # first iteration of this bucket runs eagerly (it is also the warm-up), then the graph is captured
+            self._iteration_body(bound)
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            script_it = None if self.acceptance_script is None else self.acceptance_script.snapshot()
+            with torch.cuda.graph(graph):
+                self._iteration_body(bound)
+            if script_it is not None:
+                self.acceptance_script.restore(script_it)
+            self._graphs[key] = graph
+        else:
+            g.replay()
+            torch.cuda.current_stream().synchronize()
+        accept_length, cont, new_n = (int(x) for x in self._result_host[:3])
+        self.draft_model.kv_cache.kv_offset = n + accept_length
+        self.target_model.kv_cache.kv_offset = n + accept_length
+        self.num_nodes = new_n
+        self.num_draft_tokens_this_iter = new_n
+        self.num_nodes_this_iter = new_n + N
+        self.stats["verify_calls"] += 1
+        self.last_accept_length = accept_length
+        return bool(cont)
+
     @torch.inference_mode()
     def build_tree(self):
         """Draft side (static...:257-281): one draft forward per tree level; the next level's tokens
         are the per-node top-k draft tokens gathered in growmap order."""
+        if self._graph_ok():
+            self._tree_pending = True          # the draft levels run inside verify()'s iteration graph
+            return
         n = self.num_nodes
         for step in range(self.tree_depth):
             a, b = self.level_ranges[step]
@@ -199,6 +279,9 @@ class StaticSpeculationEngine(BaseEngine):
 
     @torch.inference_mode()
     def verify(self):
+        if self._tree_pending:
+            self._tree_pending = False
+            return self._run_iteration_graph()
         n, N = self.num_nodes, self.tree_size
         ids = self.tokens[0, n:n + N]
         pos = self.position_ids[0, n:n + N]
@@ -207,7 +290,7 @@ class StaticSpeculationEngine(BaseEngine):
         if self.acceptance_script is not None:
             sampled = self.acceptance_script(self, sampled)
         ops.tree_accept(sampled, self.tokens[0], self.position_ids[0], self.parents, self.depth, n, self._eos_dev,
-                        self._result)
+                        self._result, state=self._state)
         # compaction reads (len, path) from the device result; the host only needs 4 ints afterwards
         self.draft_model.kv_cache.gather_from_result(self._result, n, 0)
         self.target_model.kv_cache.gather_from_result(self._result, n, 0)
@@ -226,10 +309,12 @@ class StaticSpeculationEngine(BaseEngine):
     @torch.inference_mode()
     def reset(self):
         self.num_nodes = 0
+        self._tree_pending = False
         self.tokens.zero_()
         self.position_ids.zero_()
         self.draft_model.clear()
         self.target_model.clear()
+        self._state.zero_()
 
     def validate_status(self):
         return self.num_nodes <= (self.max_length - self.safe_buffer)
