@@ -44,6 +44,8 @@ const char* umb_version(void);
 const char* umb_error_string(int code);
 /* Number of kernel launches issued through this library since load (all entry points). */
 unsigned long long umb_launch_count(void);
+/* A replayed CUDA graph re-issues the launches recorded at capture: the host adds them here. */
+void umb_launch_count_add(unsigned long long n);
 
 /* ------------------------------------------------------------------------------------------------
  * (i) AWQ INT4 GEMM  --  y[M,N] = x[M,K] . W,  W[k, n] = (q[k,n] - z[k/g,n]) * s[k/g,n]

@@ -48,6 +48,7 @@ SIGNATURES = {
     "umb_version": (C.c_char_p, []),
     "umb_error_string": (C.c_char_p, [c_int]),
     "umb_launch_count": (C.c_ulonglong, []),
+    "umb_launch_count_add": (None, [C.c_ulonglong]),
     "umb_awq_packed_bytes": (c_size_t, [c_int, c_int, c_int]),
     "umb_awq_repack": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                c_int, c_void_p]),

@@ -36,4 +36,6 @@ extern "C" const char* umb_error_string(int code) {
     return "unknown error";
 }
 
+extern "C" void umb_launch_count_add(unsigned long long n) { umb::g_launches.fetch_add(n, std::memory_order_relaxed); }
+
 extern "C" unsigned long long umb_launch_count(void) { return umb::g_launches.load(std::memory_order_relaxed); }

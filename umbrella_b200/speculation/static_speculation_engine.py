@@ -18,7 +18,7 @@ import time
 
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..models.auto_model import AutoModelLM
 from ..sequoia_utils import load_growmap, tree_bits_from_mask
 from .base import BaseEngine
@@ -219,13 +219,17 @@ class StaticSpeculationEngine(BaseEngine):
             torch.cuda.current_stream().synchronize()
             graph = torch.cuda.CUDAGraph()
             script_it = None if self.acceptance_script is None else self.acceptance_script.snapshot()
+            before = _lib.launch_count()
             with torch.cuda.graph(graph):
                 self._iteration_body(bound)
+            graph_launches = _lib.launch_count() - before          # kernels one replay re-issues
+            _lib.load().umb_launch_count_add(-graph_launches & 0xFFFFFFFFFFFFFFFF)   # capture itself ran nothing
             if script_it is not None:
                 self.acceptance_script.restore(script_it)
-            self._graphs[key] = graph
+            self._graphs[key] = (graph, graph_launches)
         else:
-            g.replay()
+            g[0].replay()
+            _lib.load().umb_launch_count_add(g[1])
             torch.cuda.current_stream().synchronize()
         accept_length, cont, new_n = (int(x) for x in self._result_host[:3])
         self.draft_model.kv_cache.kv_offset = n + accept_length
