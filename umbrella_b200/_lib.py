@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libumbrella_b200.so")
+# UMB_LIB_PATH selects an experiment build of the same library (umbrella_b200/build.py --variant)
+LIB_PATH = os.environ.get("UMB_LIB_PATH") or os.path.join(HERE, "libumbrella_b200.so")
 
 c_void_p, c_int, c_int64, c_size_t, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
 

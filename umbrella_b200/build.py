@@ -33,10 +33,13 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None, variant: str = "") -> str:
+    """``variant`` + ``extra_flags`` (e.g. ["-DUMB_DQ_GROUPS=4"]) build an experiment library
+    libumbrella_b200.<variant>.so next to the product one; select it with UMB_LIB_PATH."""
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    obj_dir = os.path.join(HERE, "build")
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + list(extra_flags or [])
+    obj_dir = os.path.join(HERE, "build" + (("_" + variant) if variant else ""))
+    LIB = os.path.join(HERE, f"libumbrella_b200.{variant}.so") if variant else globals()["LIB"]
     os.makedirs(obj_dir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -66,4 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    # python -m umbrella_b200.build [--force] [--variant NAME -DFOO=1 ...]
+    argv = sys.argv[1:]
+    variant = argv[argv.index("--variant") + 1] if "--variant" in argv else ""
+    print(build(force="--force" in argv, verbose=True, extra_flags=[a for a in argv if a.startswith("-D")],
+                variant=variant))

@@ -41,7 +41,10 @@ constexpr int kRecordBytes = 8512;       // 8192 nibble bytes + 256 scale bytes 
 constexpr int kRecordStride = UMB_RECORD_STRIDE;   // distance between records in the stream
 constexpr int kRecScaleOff = 8192;
 constexpr int kRecZeroOff = 8448;
-constexpr int kDqGroups = 3;              // dequant warp groups (4 warps each, one per TMEM lane quarter)
+#ifndef UMB_DQ_GROUPS
+#define UMB_DQ_GROUPS 3
+#endif
+constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each, one per TMEM lane quarter)
 constexpr int kGemmThreads = 96 + 128 * kDqGroups;   // producer + 2 MMA issuers + dequant groups (AWQ)
 constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
