@@ -189,6 +189,12 @@ int umb_probe_umma(const void* a /*fp16 [128,64]*/, const void* b /*fp16 [16,64]
                    umb_stream_t stream);
 
 
+/* Debug (tests / profiling only): with UMB_GEMM_TRACE=1 in the environment every GEMM launch records 16
+ * %globaltimer stamps per CTA (entry, set-up done, weight copies issued, dependency resolved, first record
+ * landed, first MMA, last MMA, first accumulator ready, epilogue done, exit, ...); this call synchronises the
+ * device and copies the stamps of the most recent launch, [max_ctas][16], to host memory. */
+int umb_debug_gemm_trace(unsigned long long* host_out, int max_ctas);
+
 /* Cross-check of the packed AWQ stream on CUDA cores (tests only; not a product path). */
 int umb_awq_gemm_f16_simt(const void* x, int64_t ldx, const void* packed, void* y, int64_t ldy, int M, int K, int N_total,
                           umb_stream_t stream);

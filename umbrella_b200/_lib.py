@@ -75,6 +75,7 @@ SIGNATURES = {
     "umb_embedding_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "umb_argmax_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "umb_argmax_keys_to_ids": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "umb_debug_gemm_trace": (c_int, [c_void_p, c_int]),
     "umb_probe_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "umb_awq_gemm_f16_simt": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "umb_llama_gemm_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),

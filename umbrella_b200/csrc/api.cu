@@ -1,5 +1,6 @@
 // Library bookkeeping: version, error strings, launch counter, device properties.
 #include <atomic>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -7,6 +8,14 @@
 namespace umb {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("UMB_PDL");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached != 0;
+}
 int sm_count() {
     static int cached = 0;
     if (cached == 0) {

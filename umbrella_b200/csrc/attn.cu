@@ -129,6 +129,8 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParam
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [2][kBN][D]
     __half* sV = sK + 2 * kBN * D;                                     // [2][kBN][D]
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g4 = lane >> 2, t4 = lane & 3;
@@ -385,6 +387,8 @@ __device__ __forceinline__ uint32_t row_window32(const AttnParams& p, int tok, b
 template <int D, bool kSoftCap>
 __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g4 = lane >> 2, t4 = lane & 3;
     const int hkv = blockIdx.y, split = blockIdx.z;
@@ -614,6 +618,8 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const Attn
 // grid (Hkv * qo * G); block D threads.  Merges the per-split (m, l, o) triples.
 template <int D>
 __global__ void __launch_bounds__(D) tree_attn_combine_kernel(const AttnParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int rows_total = p.qo * p.G;
     const int grow = blockIdx.x;                 // hkv * rows_total + row
     const int hkv = grow / rows_total, row = grow % rows_total;
@@ -653,7 +659,7 @@ static int launch_attn(const AttnParams& p, bool slab, dim3 grid, cudaStream_t s
             UMB_CUDA(cudaFuncSetAttribute(tree_attn_slab_kernel<D, kSoftCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_done = true;
         }
-        tree_attn_slab_kernel<D, kSoftCap><<<grid, kAttnThreads, smem, st>>>(p);
+        UMB_LAUNCH_PDL(tree_attn_slab_kernel<D, kSoftCap>, grid, dim3(kAttnThreads), smem, st, p);
     } else {
         const size_t smem = (size_t)4 * kBN * D * sizeof(__half);
         static bool attr_done = false;
@@ -661,11 +667,11 @@ static int launch_attn(const AttnParams& p, bool slab, dim3 grid, cudaStream_t s
             UMB_CUDA(cudaFuncSetAttribute(tree_attn_kernel<D, kSoftCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_done = true;
         }
-        tree_attn_kernel<D, kSoftCap><<<grid, kAttnThreads, smem, st>>>(p);
+        UMB_LAUNCH_PDL(tree_attn_kernel<D, kSoftCap>, grid, dim3(kAttnThreads), smem, st, p);
     }
     int launches = 1;
     if (p.splits > 1) {
-        tree_attn_combine_kernel<D><<<(unsigned)(p.Hkv * p.qo * p.G), D, 0, st>>>(p);
+        UMB_LAUNCH_PDL(tree_attn_combine_kernel<D>, dim3((unsigned)(p.Hkv * p.qo * p.G)), dim3(D), 0, st, p);
         launches = 2;
     }
     count_launches(launches);

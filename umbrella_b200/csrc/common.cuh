@@ -118,6 +118,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 __device__ __forceinline__ void tma_bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tma_tensor2d_prefetch_l2(const CUtensorMap* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_tensor2d_g2s(void* smem_dst, const CUtensorMap* tmap, int c0, int c1,
                                                  uint64_t* bar, uint64_t policy) {
     asm volatile(
@@ -226,6 +230,19 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float ld_cg_f32(const float* p) {

@@ -45,7 +45,7 @@ constexpr int kRecZeroOff = 8448;
 #define UMB_DQ_GROUPS 3
 #endif
 constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each, one per TMEM lane quarter)
-constexpr int kGemmThreads = 96 + 128 * kDqGroups;   // producer + 2 MMA issuers + dequant groups (AWQ)
+constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1);   // producer + 2 MMA issuers + dequant groups + epilogue group (AWQ)
 constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
 
@@ -210,8 +210,15 @@ struct GemmParams {
     int* counters;                 // [tiles]
     float* slots;                  // [tiles + grid][MPAD][128]
     int stages;                    // depth of the shared-memory ring
-    int prefetch;                  // L2 prefetch distance of the weight stream, in units (0 = off)
+    unsigned long long* trace;     // debug timeline [grid][16] (UMB_GEMM_TRACE=1), else NULL
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) : : "memory");
+    return t;
+}
+#define UMB_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
 
 template <int MPAD>
 struct GemmCfg {
@@ -272,15 +279,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
     }
     const bool n_ok = n < p.N_total;
     if (!n_ok && !(p.mode == UMB_EPI_LOGITS && p.argmax)) return;
+    const int mcols = p.M - m0;                       // valid token columns of this chunk (may exceed 16)
     const __half b = (p.bias && n_ok) ? p.bias[n] : __float2half_rn(0.f);
+    // residual rows first, all loads in flight together: y may alias residual, so a load placed after a
+    // store of the previous row would be serialised behind it (one L2 round trip per token row)
+    __half res[16];
+    if (p.mode == UMB_EPI_RESIDUAL) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < mcols) res[j] = p.residual[(int64_t)(m0 + j) * p.ld_residual + n];
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
+        if (j >= mcols) continue;
         const int m = m0 + j;
-        if (m >= p.M) break;
         __half h = __float2half_rn(v[j]);
         if (p.bias) h = __hadd(h, b);
         if (p.mode == UMB_EPI_RESIDUAL) {
-            h = __hadd(p.residual[(int64_t)m * p.ld_residual + n], h);
+            h = __hadd(res[j], h);
             reinterpret_cast<__half*>(p.y)[(int64_t)m * p.ldy + n] = h;
         } else if (p.mode == UMB_EPI_LOGITS) {
             const float f = __half2float(h);
@@ -320,12 +336,15 @@ __device__ __forceinline__ void load_acc_sum(uint32_t taddr, float (&v)[16], int
     }
 }
 
-// Warp roles (AWQ: 15 warps, fp16: 7 warps)
-//   warp 0       TMA producer
-//   warps 1, 2   MMA issuers: CTA-local unit u is issued by warp 1 + (u & 1), each into its own half of
-//                the TMEM accumulators -- the per-unit issue loop (two mbarrier waits, 8 UTCHMMA, one
-//                commit) is the serial bottleneck of a one-issuer design at 8.5 KB units
-//   warps 3..14  dequant groups (AWQ); warps 3..6 also run the epilogue
+// Warp roles (AWQ: 19 warps, fp16: 7 warps)
+//   warp 0        TMA producer.  The weight copies of the first kStages units are issued BEFORE
+//                 griddepcontrol.wait (weights never depend on the stream predecessor), the x slabs after it
+//   warps 1, 2    MMA issuers: CTA-local unit u is issued by warp 1 + (u & 1), each into its own half of
+//                 the TMEM accumulators
+//   warps 3..14   dequant groups (AWQ only): shared memory -> registers -> tensor memory; they start as
+//                 soon as a weight record has landed, also before the predecessor kernel has finished
+//   last 4 warps  epilogue only (AWQ: warps 15..18, fp16: warps 3..6): the partial-tile fix-up is a chain of
+//                 global round trips and must not stall the dequant stream
 template <int MPAD, bool kAwq>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -334,7 +353,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     const int kStages = p.stages;
     constexpr int kXBytes = kAwq ? Cfg::kXBytesAwq : Cfg::kXBytesF16;
     constexpr int kWStride = kAwq ? Cfg::kPackedStride : Cfg::kWBytesF16;
-    constexpr uint32_t kTxBytes = kAwq ? (uint32_t)(kRecordBytes + kXBytes) : (uint32_t)(Cfg::kWBytesF16 + kXBytes);
+    constexpr uint32_t kWTxBytes = kAwq ? (uint32_t)kRecordBytes : (uint32_t)Cfg::kWBytesF16;
     constexpr uint32_t kIdesc = umma_idesc_f16(kTileN, MPAD);
     constexpr int kNumAcc = Cfg::kNumAcc;                       // >= 2, even
     constexpr int kAccUsed = kAwq ? kNumAcc : (kNumAcc < 8 ? kNumAcc : 8);
@@ -348,15 +367,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     unsigned char* s_w = s_x + kStages * kXBytes;                // kStages x kWStride
     __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStride);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes);
-    uint64_t* full = bars;                    // [kStages]   TMA landed (W record + x slab)
-    uint64_t* done = bars + 16;               // [kStages]   every MMA of the unit in this stage has retired
-    uint64_t* a_full = bars + 32;             // [kAStages]  dequantised A operand is in tensor memory
-    uint64_t* acc_full = bars + 48;
-    uint64_t* acc_empty = bars + 49;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 50);
-    int* s_flag = reinterpret_cast<int*>(bars + 51);
+    uint64_t* full_w = bars;                  // [kStages]   weight record / tile landed
+    uint64_t* full_x = bars + 16;             // [kStages]   x slab landed
+    uint64_t* done = bars + 32;               // [kStages]   every MMA of the unit in this stage has retired
+    uint64_t* a_full = bars + 48;             // [kAStages]  dequantised A operand is in tensor memory
+    uint64_t* acc_full = bars + 56;
+    uint64_t* acc_empty = bars + 57;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 58);
+    int* s_flag = reinterpret_cast<int*>(bars + 59);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) UMB_TRACE(0);
     const long long U = (long long)p.tiles * p.units_per_tile, P = gridDim.x;
     const long long u_begin = sk_begin(blockIdx.x, U, P), u_end = sk_begin(blockIdx.x + 1, U, P);
     const int n_units = (int)(u_end - u_begin);
@@ -367,7 +388,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         tma_prefetch_desc(&tmap_x);
         if (!kAwq) tma_prefetch_desc(&tmap_w);
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(full + i, 1);
+            mbar_init(full_w + i, 1);
+            mbar_init(full_x + i, 1);
             mbar_init(done + i, 1);
         }
         for (int i = 0; i < kAStages; ++i) mbar_init(a_full + i, 4);
@@ -382,36 +404,75 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
+    if (threadIdx.x == 0) UMB_TRACE(1);
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
         const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
-        Ring r;
-        int tile = tile0, g = in_tile0;
         const unsigned char* src = p.packed + (kAwq ? u_begin * kRecordStride : 0);
-        for (int i = 0; i < n_units; ++i, ++g) {
-            if (g == p.units_per_tile) {
+        const int n_pre = n_units < kStages ? n_units : kStages;
+        int tile = tile0, g = in_tile0;                          // (tile, g) of the next weight copy
+        for (int i = 0; i < n_pre; ++i) {                        // weights first: independent of the predecessor
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_w + i, kWTxBytes);
+                if constexpr (kAwq)
+                    tma_bulk_g2s(s_w + i * kWStride, src, kRecordBytes, full_w + i, pol_w);
+                else
+                    tma_tensor2d_g2s(s_w + i * kWStride, &tmap_w, g * 64, tile * kTileN, full_w + i, pol_w);
+            }
+            __syncwarp();
+            src += kRecordStride;
+            if (++g == p.units_per_tile) {
                 g = 0;
                 ++tile;
             }
+        }
+        if (lane == 0) UMB_TRACE(2);
+        pdl_wait();                                              // x is the predecessor's output
+        if (lane == 0) UMB_TRACE(3);
+        int gx = in_tile0;
+        for (int i = 0; i < n_pre; ++i) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_x + i, (uint32_t)kXBytes);
+                unsigned char* xs = s_x + i * kXBytes;
+                if constexpr (kAwq) {
+                    tma_tensor2d_g2s(xs, &tmap_x, gx * kGroup, 0, full_x + i, pol_x);
+                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, gx * kGroup + 64, 0, full_x + i, pol_x);
+                } else {
+                    tma_tensor2d_g2s(xs, &tmap_x, gx * 64, 0, full_x + i, pol_x);
+                }
+            }
+            __syncwarp();
+            if (++gx == p.units_per_tile) gx = 0;
+        }
+        Ring r;
+        r.phase = 1;                                             // every stage has been used once
+        for (int i = n_pre; i < n_units; ++i) {
             mbar_wait(done + r.stage, r.phase ^ 1);              // the unit that last used this stage has retired
             if (elect_one()) {
-                mbar_arrive_expect_tx(full + r.stage, kTxBytes);
+                mbar_arrive_expect_tx(full_w + r.stage, kWTxBytes);
+                mbar_arrive_expect_tx(full_x + r.stage, (uint32_t)kXBytes);
                 unsigned char* xs = s_x + r.stage * kXBytes;
                 if constexpr (kAwq) {
-                    tma_bulk_g2s(s_w + r.stage * kWStride, src, kRecordBytes, full + r.stage, pol_w);
-                    tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full + r.stage, pol_x);
-                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full + r.stage, pol_x);
+                    tma_bulk_g2s(s_w + r.stage * kWStride, src, kRecordBytes, full_w + r.stage, pol_w);
+                    tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full_x + r.stage, pol_x);
+                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full_x + r.stage, pol_x);
                 } else {
-                    tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full + r.stage, pol_w);
-                    tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full + r.stage, pol_x);
+                    tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full_w + r.stage, pol_w);
+                    tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full_x + r.stage, pol_x);
                 }
             }
             __syncwarp();
             src += kRecordStride;
+            if (++g == p.units_per_tile) {
+                g = 0;
+                ++tile;
+            }
             r.advance(kStages);
         }
+        if (lane == 0) UMB_TRACE(10);
     } else if (warp <= 2) {
         // ===================== MMA issuers: warp 1 takes even CTA-local units, warp 2 odd ones =====================
         const int par = warp - 1;
@@ -429,9 +490,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const bool last = u + 2 >= seg_end;
                 if constexpr (kAwq) {
                     mbar_wait(a_full + ts, pa);
+                } else {
+                    mbar_wait(full_w + st, ph);
                 }
-                mbar_wait(full + st, ph);
+                mbar_wait(full_x + st, ph);
                 tc_fence_after();
+                if (u == 0 && lane == 0) UMB_TRACE(5);
                 const uint32_t xs = smem_u32(s_x + st * kXBytes);
                 const uint64_t bd0 = kDescHi | (uint64_t)((xs & 0x3FFFF) >> 4);
                 if constexpr (kAwq) {
@@ -479,23 +543,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             in_tile = 0;
             ++seg;
         }
+        if (par == 0 && lane == 0) UMB_TRACE(6);
     } else {
-        // ===================== dequant (AWQ) + epilogue warps =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may touch
-        const int grp = (warp - 3) >> 2;             // dequant group 0..kDqGroups-1; group 0 also runs the epilogue
-        const bool is_epi = grp == 0;
+        const int grp = (warp - 3) >> 2;             // AWQ: dequant group 0..kDqGroups-1, then the epilogue group
+        const bool is_epi = kAwq ? (grp == kDqGroups) : true;
         const int fl = q * 32 + lane;                // feature lane 0..127
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        int seg = 0, seg_begin = 0, in_tile = in_tile0, tile = tile0;
-        int mine = grp;                              // CTA-local index of this group's next unit
-        int dq_st = grp % kStages, dq_ph = 0, dq_ts = grp % kAStages;      // ring positions of unit `mine`
-        int w_first = grp;                                                 // first unit of this group that re-uses a TMEM stage
-        while (w_first < kAStages) w_first += kDqGroups;
-        int w_st = (w_first - kAStages) % kStages, w_ph = 0;               // ring position of unit `mine - kAStages`
-        while (seg_begin < n_units) {
-            const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
+        if (!is_epi) {
+            // ===================== dequant warps (AWQ): group g takes CTA-local units g, g + kDqGroups, ... =====================
             if constexpr (kAwq) {
-                for (; mine < seg_end; mine += kDqGroups) {
+                int dq_st = grp % kStages, dq_ph = 0, dq_ts = grp % kAStages;      // ring positions of unit `mine`
+                int w_first = grp;                                                 // first unit of this group that re-uses a TMEM stage
+                while (w_first < kAStages) w_first += kDqGroups;
+                int w_st = (w_first - kAStages) % kStages, w_ph = 0;               // ring position of unit `mine - kAStages`
+                for (int mine = grp; mine < n_units; mine += kDqGroups) {
                     const int st = dq_st, ph = dq_ph, ts = dq_ts;
                     dq_st += kDqGroups;
                     if (dq_st >= kStages) {
@@ -504,7 +566,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     }
                     dq_ts += kDqGroups;
                     if (dq_ts >= kAStages) dq_ts -= kAStages;
-                    mbar_wait(full + st, ph);
+                    mbar_wait(full_w + st, ph);
+                    if (mine == 0 && q == 0 && lane == 0) UMB_TRACE(4);
                     const uint32_t rec = smem_u32(s_w + st * kWStride);
                     uint4 w4[4];
 #pragma unroll
@@ -541,7 +604,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     if (lane == 0) mbar_arrive(a_full + ts);
                 }
             }
-            if (is_epi) {
+        } else {
+            // ===================== epilogue warps =====================
+            const int ew = kAwq ? warp - 3 - 4 * kDqGroups : warp - 3;       // 0..3 inside the epilogue group
+            pdl_wait();                                  // residual / workspace / y belong to the predecessors
+            if (ew == 0 && lane == 0) UMB_TRACE(11);
+            int seg = 0, seg_begin = 0, in_tile = in_tile0, tile = tile0;
+            while (seg_begin < n_units) {
+                const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
                 const int seg_len = seg_end - seg_begin;
                 const bool whole = seg_len == p.units_per_tile;
                 // which MMA warps issued into their accumulators during this segment
@@ -549,6 +619,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const int use_mask = ((seg_len - n_odd) > 0 ? 1 : 0) | (n_odd > 0 ? 2 : 0);
                 mbar_wait(acc_full, seg & 1);
                 tc_fence_after();
+                if (ew == 0 && lane == 0) UMB_TRACE(seg == 0 ? 7 : 12);
                 if (whole) {
 #pragma unroll 1
                     for (int m0 = 0; m0 < MPAD; m0 += 16) {
@@ -562,65 +633,120 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         if (m0 < p.M || p.mode == UMB_EPI_SILU_MUL) epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
                     }
                 } else {
-                    // partial tile: publish to this CTA's slot, the last arriver reduces in slot order
-                    float* slot = p.slots + ((size_t)tile + blockIdx.x) * (MPAD * kTileN);
-#pragma unroll 1
-                    for (int m0 = 0; m0 < MPAD; m0 += 16) {
-                        float v[16];
-                        load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v, use_mask);
-                        if (m0 + 16 >= MPAD) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(acc_empty);
-                        }
-                        if (m0 < p.M) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) slot[(m0 + j) * kTileN + fl] = v[j];
-                        }
-                    }
-                    __threadfence();
-                    named_bar_sync(1, 128);
+                    // Partial tile.  The CTA that owns the HEAD of the tile (c_first; that part is the last
+                    // segment of its range) is the reducer; every other part is the FIRST segment of its owner,
+                    // i.e. published early in the kernel.  Publication needs no fence, counter or barrier: every
+                    // 32-bit word of a slot is its own flag (0 = not yet written; a partial sum of +0.0f is stored
+                    // as -0.0f, which adds identically), the reducer polls exactly the words it needs with relaxed
+                    // gpu-scope loads, adds them to its own partial (kept in registers) in ascending CTA order --
+                    // deterministic -- and stores the zeros back, which leaves the workspace clean for the next
+                    // launch.  Only one L2 round trip of the reducer sits on the kernel's tail.
                     const long long tile_u0 = (long long)tile * p.units_per_tile;
                     const int c_first = sk_owner(tile_u0, U, P);
                     const int c_last = sk_owner(tile_u0 + p.units_per_tile - 1, U, P);
-                    if (warp == 3 && lane == 0) {
-                        const int old = atomicAdd(p.counters + tile, 1);
-                        const int last = (old == c_last - c_first) ? 1 : 0;
-                        if (last) p.counters[tile] = 0;
-                        *s_flag = last;
-                    }
-                    named_bar_sync(1, 128);
-                    const bool is_last = *s_flag != 0;
-                    named_bar_sync(1, 128);          // s_flag may be rewritten by the next segment
-                    if (is_last) {
-                        __threadfence();
+                    if ((int)blockIdx.x != c_first) {
+                        uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots) + ((size_t)tile + blockIdx.x) * (MPAD * kTileN);
 #pragma unroll 1
                         for (int m0 = 0; m0 < MPAD; m0 += 16) {
-                            if (!(m0 < p.M || p.mode == UMB_EPI_SILU_MUL)) break;
                             float v[16];
+                            load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v, use_mask);
+                            if (m0 + 16 >= MPAD) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(acc_empty);
+                            }
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                            if (m0 < p.M) {
-                                for (int c = c_first; c <= c_last; ++c) {
-                                    const float* sl = p.slots + ((size_t)tile + c) * (MPAD * kTileN);
+                            for (int j = 0; j < 16; ++j)
+                                if (m0 + j < p.M) {
+                                    const uint32_t u = __float_as_uint(v[j]);
+                                    slot[(m0 + j) * kTileN + fl] = u ? u : 0x80000000u;
+                                }
+                        }
+                    } else {
+                        const int n_other = c_last - c_first;
+#pragma unroll 1
+                        for (int m0 = 0; m0 < MPAD; m0 += 16) {
+                            float v[16];
+                            load_acc_sum<kAccUsed, MPAD>(tmem_base + lane_addr + m0, v, use_mask);
+                            if (m0 + 16 >= MPAD) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(acc_empty);
+                            }
+                            if (!(m0 < p.M || p.mode == UMB_EPI_SILU_MUL)) continue;
+                            const int mcols = p.M - m0;
+                            uint32_t* sl0 = reinterpret_cast<uint32_t*>(p.slots) +
+                                            ((size_t)tile + c_first + 1) * (MPAD * kTileN) + m0 * kTileN + fl;
+                            if (mcols <= 4) {
+                                // few token rows (draft levels): 8 slots in flight per round trip
+                                for (int c0 = 0; c0 < n_other; c0 += 8) {
+                                    uint32_t t[8][4];
+                                    bool pending;
+                                    do {
+                                        pending = false;
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j) v[j] += ld_cg_f32(sl + (m0 + j) * kTileN + fl);
+                                        for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+                                            for (int j = 0; j < 4; ++j) {
+                                                const bool need = c0 + cc < n_other && j < mcols;
+                                                t[cc][j] = need ? ld_relaxed_gpu_u32(sl0 + (size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN) : 0x80000000u;
+                                            }
+#pragma unroll
+                                        for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+                                            for (int j = 0; j < 4; ++j) pending |= t[cc][j] == 0u;
+                                    } while (pending);
+#pragma unroll
+                                    for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            v[j] += __uint_as_float(t[cc][j]);
+                                            if (c0 + cc < n_other && j < mcols) sl0[(size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN] = 0u;
+                                        }
+                                }
+                            } else if (mcols > 0) {
+                                for (int c0 = 0; c0 < n_other; c0 += 2) {
+                                    uint32_t t[2][16];
+                                    bool pending;
+                                    do {
+                                        pending = false;
+#pragma unroll
+                                        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                                            for (int j = 0; j < 16; ++j) {
+                                                const bool need = c0 + cc < n_other && j < mcols;
+                                                t[cc][j] = need ? ld_relaxed_gpu_u32(sl0 + (size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN) : 0x80000000u;
+                                            }
+#pragma unroll
+                                        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                                            for (int j = 0; j < 16; ++j) pending |= t[cc][j] == 0u;
+                                    } while (pending);
+#pragma unroll
+                                    for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                                        for (int j = 0; j < 16; ++j) {
+                                            v[j] += __uint_as_float(t[cc][j]);
+                                            if (c0 + cc < n_other && j < mcols) sl0[(size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN] = 0u;
+                                        }
                                 }
                             }
                             epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
                         }
                     }
                 }
+                seg_begin = seg_end;
+                in_tile = 0;
+                ++tile;
+                ++seg;
+                if (ew == 0 && lane == 0) UMB_TRACE(seg == 1 ? 8 : 13);
             }
-            seg_begin = seg_end;
-            in_tile = 0;
-            ++tile;
-            ++seg;
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) UMB_TRACE(9);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -763,6 +889,19 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
     return r == CUDA_SUCCESS ? UMB_OK : UMB_ERR_ARG;
 }
 
+// debug timeline (UMB_GEMM_TRACE=1): one device buffer, 16 stamps per CTA of the LAST gemm launch
+static unsigned long long* trace_buffer() {
+    static unsigned long long* buf = nullptr;
+    static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        const char* e = getenv("UMB_GEMM_TRACE");
+        if (e && e[0] == '1' && cudaMalloc(&buf, 1024 * 16 * sizeof(unsigned long long)) != cudaSuccess) buf = nullptr;
+        if (buf) cudaMemset(buf, 0, 1024 * 16 * sizeof(unsigned long long));
+    }
+    return buf;
+}
+
 static int mpad_of(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128)); }
 
 template <int MPAD, bool kAwq>
@@ -775,22 +914,17 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, GemmParams 
             env_stages = e ? atoi(e) : 0;
         }
         if (env_stages > 0 && env_stages <= 16 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024) p.stages = env_stages;
-        static int env_pf = -1;
-        if (env_pf < 0) {
-            const char* e = getenv("UMB_GEMM_PREFETCH");
-            env_pf = e ? atoi(e) : 0;
-        }
-        p.prefetch = env_pf;
     }
+    p.trace = trace_buffer();
     const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages);
     static int attr_smem = 0;
     if (attr_smem < smem) {
         UMB_CUDA(cudaFuncSetAttribute(gemm_kernel<MPAD, kAwq>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
-    gemm_kernel<MPAD, kAwq><<<grid, kAwq ? kGemmThreads : kGemmThreadsF16, smem, st>>>(tx, tw, p);
+    UMB_LAUNCH_PDL(gemm_kernel<MPAD, kAwq>, dim3(grid), dim3(kAwq ? kGemmThreads : kGemmThreadsF16), (size_t)smem, st, tx,
+                   tw, p);
     count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
 
@@ -826,6 +960,13 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     if (U >= (1ll << 31)) return UMB_ERR_UNSUPPORTED;
     int grid = sm_count();
     if ((long long)grid > U) grid = (int)U;
+    if (U < 16ll * grid && p.tiles <= grid) {
+        // small problem (draft-model linears): latency-bound, so cut every tile into the same power-of-two
+        // number of k-slices (one segment per CTA, fewer partials per tile to reduce) instead of balancing units
+        int S = 1;
+        while (p.tiles * (S * 2) <= grid && p.units_per_tile % (S * 2) == 0) S *= 2;
+        grid = p.tiles * S;
+    }
     const size_t need = umb_gemm_workspace_bytes(M, K, N_total);
     if (!workspace || workspace_bytes < need) return UMB_ERR_WORKSPACE;
     UMB_CHECK_ARG(((uintptr_t)workspace & 15) == 0);
@@ -928,6 +1069,15 @@ extern "C" int umb_gemm_f16(const void* x, int64_t ldx, const void* w, int64_t l
                             umb_stream_t stream) {
     return gemm_common(false, x, ldx, w, ldw, y, ldy, M, K, N, epilogue, workspace, workspace_bytes,
                        (cudaStream_t)stream);
+}
+
+extern "C" int umb_debug_gemm_trace(unsigned long long* host_out, int max_ctas) {
+    unsigned long long* buf = trace_buffer();
+    if (!buf || !host_out || max_ctas < 1) return UMB_ERR_ARG;
+    if (max_ctas > 1024) max_ctas = 1024;
+    UMB_CUDA(cudaDeviceSynchronize());
+    UMB_CUDA(cudaMemcpy(host_out, buf, (size_t)max_ctas * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return UMB_OK;
 }
 
 extern "C" int umb_probe_umma(const void* a, const void* b, float* d, int mode, umb_stream_t stream) {

@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int hidden,
                float eps) {
     __shared__ float s_part[kNormThreads / 32];
+    pdl_launch_dependents();
+    pdl_wait();
     const __half* xr = x + (int64_t)blockIdx.x * hidden;
     __half* yr = y + (int64_t)blockIdx.x * hidden;
     const int vecs = hidden >> 3;
@@ -94,6 +96,8 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
 __global__ void embedding_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ ids_offset_dev,
                                  int ids_offset_add, const __half* __restrict__ table, __half* __restrict__ y,
                                  int hidden) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t off = ids_offset_dev ? (int64_t)ids_offset_dev[0] + ids_offset_add : 0;
     const int64_t id = ids[off + blockIdx.x];
     const uint4* src = reinterpret_cast<const uint4*>(table + id * hidden);
@@ -112,6 +116,8 @@ __global__ void rope_append_kernel(const __half* __restrict__ qkv, int64_t ld_qk
                                    int Hq, int Hkv, int D, int64_t kv_tok_stride, int64_t kv_head_stride,
                                    int kv_offset_host, const int32_t* __restrict__ kv_offset_dev) {
     // with the device words: kv row / position index = dev[0] + host offset
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x, h = blockIdx.y, d = threadIdx.x, half_d = D >> 1;
     const __half* src = qkv + (int64_t)t * ld_qkv + (int64_t)h * D;
     const int kv_offset = kv_offset_dev ? kv_offset_dev[0] + kv_offset_host : kv_offset_host;
@@ -171,6 +177,8 @@ argmax_keys_kernel(const float* __restrict__ logits, int64_t ld, int vocab, unsi
 }
 // decode keys -> int64 ids and leave the key buffer zeroed for the next use
 __global__ void argmax_decode_kernel(unsigned long long* keys, int rows, int64_t* out, int reset_keys) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const unsigned long long k = keys[r];
@@ -186,10 +194,9 @@ extern "C" int umb_rmsnorm_f16(const void* x, const void* weight, void* y, int r
                                umb_stream_t stream) {
     UMB_CHECK_ARG(x && weight && y && rows >= 1 && hidden >= 8 && (hidden % 8) == 0);
     UMB_CHECK_ARG((((uintptr_t)x | (uintptr_t)weight | (uintptr_t)y) & 15) == 0);
-    rmsnorm_kernel<<<rows, kNormThreads, 0, (cudaStream_t)stream>>>((const __half*)x, (const __half*)weight,
-                                                                     (__half*)y, hidden, eps);
+    UMB_LAUNCH_PDL(rmsnorm_kernel, dim3(rows), dim3(kNormThreads), 0, (cudaStream_t)stream, (const __half*)x,
+                   (const __half*)weight, (__half*)y, hidden, eps);
     count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
 
@@ -219,29 +226,28 @@ extern "C" int umb_embedding_f16(const int64_t* ids, const void* table, void* y,
                                  umb_stream_t stream) {
     UMB_CHECK_ARG(ids && table && y && rows >= 1 && hidden >= 8 && (hidden % 8) == 0);
     UMB_CHECK_ARG((((uintptr_t)table | (uintptr_t)y) & 15) == 0);
-    embedding_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(ids, nullptr, 0, (const __half*)table, (__half*)y, hidden);
+    UMB_LAUNCH_PDL(embedding_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, ids, (const int32_t*)nullptr, 0,
+                   (const __half*)table, (__half*)y, hidden);
     count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
 
 namespace umb {
 int embedding_dyn(const int64_t* ids_base, const int32_t* n_dev, int offset, const void* table, void* y, int rows,
                   int hidden, cudaStream_t st) {
-    embedding_kernel<<<rows, 256, 0, st>>>(ids_base, n_dev, offset, (const __half*)table, (__half*)y, hidden);
+    UMB_LAUNCH_PDL(embedding_kernel, dim3(rows), dim3(256), 0, st, ids_base, n_dev, offset, (const __half*)table,
+                   (__half*)y, hidden);
     count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
 // position_ids is the BASE pointer; rows are read at n_dev[0] + offset + t and appended at the same cache rows
 int rope_append_dyn(const void* qkv, int64_t ld_qkv, void* q_out, void* k_cache, void* v_cache, const void* cos,
                     const void* sin, const int64_t* position_base, const int32_t* n_dev, int offset, int qo, int Hq,
                     int Hkv, int D, int64_t kv_tok_stride, int64_t kv_head_stride, cudaStream_t st) {
-    rope_append_kernel<<<dim3(qo, Hq + 2 * Hkv), D / 2, 0, st>>>(
-        (const __half*)qkv, ld_qkv, (__half*)q_out, (__half*)k_cache, (__half*)v_cache, (const __half*)cos,
-        (const __half*)sin, position_base, n_dev, Hq, Hkv, D, kv_tok_stride, kv_head_stride, offset, n_dev);
+    UMB_LAUNCH_PDL(rope_append_kernel, dim3(qo, Hq + 2 * Hkv), dim3(D / 2), 0, st, (const __half*)qkv, ld_qkv,
+                   (__half*)q_out, (__half*)k_cache, (__half*)v_cache, (const __half*)cos, (const __half*)sin,
+                   position_base, n_dev, Hq, Hkv, D, kv_tok_stride, kv_head_stride, offset, n_dev);
     count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
 }  // namespace umb
@@ -254,12 +260,11 @@ extern "C" int umb_rope_append_f16(const void* qkv, int64_t ld_qkv, void* q_out,
     UMB_CHECK_ARG(qkv && q_out && k_cache && v_cache && cos && sin && position_ids);
     UMB_CHECK_ARG(qo >= 1 && num_q_heads >= 1 && num_kv_heads >= 1 && kv_offset >= 0);
     if (head_dim < 2 || head_dim > 512 || (head_dim & 1)) return UMB_ERR_UNSUPPORTED;
-    rope_append_kernel<<<dim3(qo, num_q_heads + 2 * num_kv_heads), head_dim / 2, 0, (cudaStream_t)stream>>>(
-        (const __half*)qkv, ld_qkv, (__half*)q_out, (__half*)k_cache, (__half*)v_cache, (const __half*)cos,
-        (const __half*)sin, position_ids, nullptr, num_q_heads, num_kv_heads, head_dim, kv_tok_stride, kv_head_stride,
-        kv_offset, kv_offset_dev);
+    UMB_LAUNCH_PDL(rope_append_kernel, dim3(qo, num_q_heads + 2 * num_kv_heads), dim3(head_dim / 2), 0,
+                   (cudaStream_t)stream, (const __half*)qkv, ld_qkv, (__half*)q_out, (__half*)k_cache, (__half*)v_cache,
+                   (const __half*)cos, (const __half*)sin, position_ids, (const int32_t*)nullptr, num_q_heads,
+                   num_kv_heads, head_dim, kv_tok_stride, kv_head_stride, kv_offset, kv_offset_dev);
     count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
 
@@ -279,9 +284,8 @@ extern "C" int umb_argmax_f32(const float* logits, int64_t ld, int rows, int voc
 extern "C" int umb_argmax_keys_to_ids(const unsigned long long* keys, int rows, int64_t* out, umb_stream_t stream) {
     UMB_CHECK_ARG(keys && out && rows >= 1);
     UMB_CHECK_ARG((const void*)keys != (const void*)out);
-    argmax_decode_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(const_cast<unsigned long long*>(keys),
-                                                                              rows, out, 1);
+    UMB_LAUNCH_PDL(argmax_decode_kernel, dim3((rows + 127) / 128), dim3(128), 0, (cudaStream_t)stream,
+                   const_cast<unsigned long long*>(keys), rows, out, 1);
     count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }

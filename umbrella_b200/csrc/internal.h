@@ -4,7 +4,31 @@
 
 #include "../../include/umbrella_b200.h"
 
+#include <utility>
+
 namespace umb {
+// Programmatic dependent launch (PDL): every kernel of the forward chain is launched with the
+// programmatic-stream-serialization attribute, so its CTAs may start (barrier init, TMEM allocation,
+// weight TMA + dequantisation -- nothing that depends on the predecessor) while the stream predecessor
+// is still draining.  Each such kernel executes griddepcontrol.wait before touching global memory a
+// predecessor wrote, and before completing (transitivity of the chain).  UMB_PDL=0 disables it.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define UMB_LAUNCH_PDL(...) do { cudaError_t e__ = umb::launch_pdl(__VA_ARGS__); if (e__ != cudaSuccess) return (int)e__; } while (0)
 // every host entry point reports the kernels it enqueued (umb_launch_count)
 void count_launches(unsigned n);
 // number of SMs of the current device (cached)

@@ -30,6 +30,8 @@ tree_accept_kernel(const int64_t* __restrict__ sampled, int64_t* __restrict__ to
     __shared__ int s_warp_cnt[kAcceptThreads / 32];
     __shared__ int s_len, s_eos_pos;
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = threadIdx.x;
     const int n = state ? state[0] : num_nodes_host;
     const int lane = i & 31, warp = i >> 5;
@@ -119,6 +121,8 @@ __global__ void __launch_bounds__(256)
 kv_gather_kernel(unsigned char* __restrict__ k_cache, unsigned char* __restrict__ v_cache, int64_t plane_stride,
                  int64_t row_stride, int row_bytes, const int32_t* __restrict__ result, int offset_host,
                  const int32_t* __restrict__ offset_dev, int zero_upto) {
+    pdl_launch_dependents();
+    pdl_wait();
     unsigned char* base = (blockIdx.y == 0 ? k_cache : v_cache) + (int64_t)blockIdx.x * plane_stride;
     const int len = result[0];
     const int offset = offset_dev ? offset_dev[0] : offset_host;
@@ -150,10 +154,9 @@ extern "C" int umb_tree_accept(const int64_t* sampled, int64_t* tokens, int64_t*
     UMB_CHECK_ARG(sampled && tokens && position_ids && parents && depth && result);
     UMB_CHECK_ARG(N >= 1 && num_nodes >= 0 && n_eos >= 0 && (n_eos == 0 || eos));
     if (N >= umb::kMaxTree) return UMB_ERR_UNSUPPORTED;
-    umb::tree_accept_kernel<<<1, umb::kAcceptThreads, 0, (cudaStream_t)stream>>>(
-        sampled, tokens, position_ids, parents, depth, N, num_nodes, state, eos, n_eos, result);
+    UMB_LAUNCH_PDL(umb::tree_accept_kernel, dim3(1), dim3(umb::kAcceptThreads), 0, (cudaStream_t)stream, sampled, tokens,
+                   position_ids, parents, depth, N, num_nodes, state, eos, n_eos, result);
     umb::count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
 
@@ -164,17 +167,18 @@ extern "C" int umb_kv_gather(void* k_cache, void* v_cache, int num_planes, int64
     UMB_CHECK_ARG(row_bytes > 0 && (row_bytes % 16) == 0 && (row_stride_bytes % 16) == 0 && (plane_stride_bytes % 16) == 0);
     UMB_CHECK_ARG((((uintptr_t)k_cache | (uintptr_t)v_cache) & 15) == 0);
     const int threads = row_bytes / 16 >= 256 ? 256 : (row_bytes / 16 >= 128 ? 128 : 64);
-    umb::kv_gather_kernel<<<dim3(num_planes, 2), threads, 0, (cudaStream_t)stream>>>(
-        (unsigned char*)k_cache, (unsigned char*)v_cache, plane_stride_bytes, row_stride_bytes, row_bytes, result,
-        offset, offset_dev, zero_upto);
+    UMB_LAUNCH_PDL(umb::kv_gather_kernel, dim3(num_planes, 2), dim3(threads), 0, (cudaStream_t)stream,
+                   (unsigned char*)k_cache, (unsigned char*)v_cache, plane_stride_bytes, row_stride_bytes, row_bytes,
+                   result, offset, offset_dev, zero_upto);
     umb::count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
 
 namespace umb {
 __global__ void store_tokens_kernel(int64_t* __restrict__ tokens, const int32_t* __restrict__ n_dev, int offset,
                                     const int64_t* __restrict__ src, int count) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) tokens[(int64_t)n_dev[0] + offset + i] = src[i];
 }
@@ -183,8 +187,8 @@ __global__ void store_tokens_kernel(int64_t* __restrict__ tokens, const int32_t*
 extern "C" int umb_store_tokens(int64_t* tokens_base, const int32_t* n_dev, int offset, const int64_t* src, int count,
                                 umb_stream_t stream) {
     UMB_CHECK_ARG(tokens_base && n_dev && src && count >= 1 && offset >= 0);
-    umb::store_tokens_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(tokens_base, n_dev, offset, src, count);
+    UMB_LAUNCH_PDL(umb::store_tokens_kernel, dim3((count + 127) / 128), dim3(128), 0, (cudaStream_t)stream, tokens_base,
+                   n_dev, offset, src, count);
     umb::count_launches(1);
-    UMB_LAUNCH_CHECK();
     return UMB_OK;
 }
