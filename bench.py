@@ -180,15 +180,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
 
-    t = torch.tensor([dev_ms, float(tokens), e2e_s, float(e2e_tokens)], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = t.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms_max, tokens_all, e2e_s_max, e2e_tokens_all = float(mx[0]), float(sm[1]), float(mx[2]), float(sm[3])
-    else:
-        dev_ms_max, tokens_all, e2e_s_max, e2e_tokens_all = dev_ms, float(tokens), e2e_s, float(e2e_tokens)
+    from umbrella_b200.replicas import reduce_over_replicas
+    (dev_ms_max, e2e_s_max), (tokens_all, e2e_tokens_all) = reduce_over_replicas(
+        [dev_ms, e2e_s], [float(tokens), float(e2e_tokens)], device=dev)
 
     if rank == 0:
         peak, peak_src = _peaks()

@@ -172,6 +172,18 @@ int umb_kv_gather(void* k_cache, void* v_cache, int num_planes, int64_t plane_st
                   int row_bytes, const int32_t* result, int offset, const int32_t* offset_dev, int zero_upto,
                   umb_stream_t stream);
 
+/* One level of the dynamic (SpecExec-style) tree builder -- DynamicSpeculationEngine.build_tree,
+ * reference umbrella/speculation/dynamic_speculation_engine.py:231-248 -- after the draft's top-`beams`
+ * logits of the level's `rows` nodes (tree ids [level_first, level_first + rows)) have been selected:
+ *   cand[r, b] = tree_score[level_first + r] + log(softmax(topk_logits[r, :])[b] + 1e-4)   (fp32)
+ *   the `width` best candidates, best first, become nodes level_first + rows + j:
+ *   tree_score[id], tokens[n + id] = topk_ids[flat], parents[id] = level_first + flat / beams,
+ *   tree_bits[id, :] = tree_bits[parent, :] | bit id.
+ * n = n_dev[0] if n_dev != NULL (device int32) else num_nodes.  rows <= 128, rows * beams <= 4096. */
+int umb_dyn_tree_expand(const float* topk_logits, const int64_t* topk_ids, int rows, int beams, int width,
+                        int level_first, int num_nodes, const int32_t* n_dev, float* tree_score, int64_t* tokens,
+                        int32_t* parents, uint32_t* tree_bits, int tree_words, umb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * glue
  * ---------------------------------------------------------------------------------------------- */
@@ -254,6 +266,16 @@ size_t umb_llama_gemm_ws_bytes(int hidden, int intermediate, int num_q_heads, in
 int umb_llama_forward(const umb_llama_t* model, const int64_t* input_ids, const int64_t* position_ids, int rows,
                       int kv_offset, const umb_attn_mask_t* mask, float* logits, int logits_from_row,
                       unsigned long long* argmax_keys, umb_stream_t stream);
+
+/* Layer-range slice of umb_llama_forward for paged (host-offloaded) weights -- the seam of the
+ * reference's LlamaOffload.inference loop (umbrella/models/llama.py:196-219): the caller runs layers
+ * [layer_begin, layer_end) of rows <= 128 (hidden state kept in model->hidden between calls), waiting on
+ * its own weight-copy events in between.  do_embed != 0 starts from the embedding (first slice);
+ * logits != NULL finishes with the final norm + lm_head (last slice; layer_begin == layer_end ==
+ * num_layers runs the head alone). */
+int umb_llama_forward_range(const umb_llama_t* model, const int64_t* input_ids, const int64_t* position_ids, int rows,
+                            int kv_offset, const umb_attn_mask_t* mask, int layer_begin, int layer_end, int do_embed,
+                            float* logits, int logits_from_row, unsigned long long* argmax_keys, umb_stream_t stream);
 
 /* Graph-replay form of the tree forward: every position-dependent quantity is read on the device
  * from n_dev[0] (the committed prefix length n, maintained by umb_tree_accept through `state`):

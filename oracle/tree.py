@@ -333,3 +333,57 @@ def scripted_samples(successors: list[list[int]], spec_tokens: np.ndarray, rng: 
                 t = int(rng.integers(3, vocab_hi))
             sampled[v] = t
     return sampled
+
+
+# --------------------------------------------------------------------------------------
+# dynamic (SpecExec-style) tree growth
+# --------------------------------------------------------------------------------------
+def dynamic_tree_level(top_logits: np.ndarray, token_ids: np.ndarray, score_history: np.ndarray, width: int):
+    """One level of DynamicSpeculationEngine.build_tree after ``draft_logits.topk(num_beams)``
+    (umbrella/speculation/dynamic_speculation_engine.py:235-245), fp32 as the reference computes it.
+
+    top_logits / token_ids  [dec_len, num_beams]  the draft's top-``num_beams`` logits and their ids
+    score_history           [dec_len]             tree_score of the level's nodes
+    Returns (score[width] fp32, tokens[width] int64, parent_row[width] int64 = index into the level),
+    best candidate first (torch.topk order; equal scores keep the lower flat index first).
+    """
+    x = np.asarray(top_logits, dtype=np.float32)
+    e = np.exp(x - x.max(axis=-1, keepdims=True), dtype=np.float32)
+    p = (e / e.sum(axis=-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+    cand = (np.asarray(score_history, dtype=np.float32)[:, None] + np.log(p + np.float32(1e-4), dtype=np.float32))
+    cand = cand.astype(np.float32).reshape(-1)
+    order = np.argsort(-cand, kind="stable")[:width]
+    beams = x.shape[1]
+    return cand[order], np.asarray(token_ids).reshape(-1)[order].astype(np.int64), (order // beams).astype(np.int64)
+
+
+def dynamic_build_tree(draft_logits_fn, tokens: np.ndarray, num_nodes: int, width: int, num_beams: int, depth: int):
+    """DynamicSpeculationEngine.build_tree (dynamic_speculation_engine.py:215-248) over a draft model given
+    as ``draft_logits_fn(token_ids int64[q]) -> fp32 [q, V]`` (a context-free model is enough for the tree
+    bookkeeping; the reference's forward also takes positions / mask / KV).
+
+    Mutates ``tokens[num_nodes + 1 : num_nodes + N]``; returns (parents int32[N], tree_mask bool[N, N],
+    tree_score fp32[N]) exactly as the reference leaves ``self.parents``, the tree block of
+    ``attn_mask_this_iter`` and ``self.tree_score`` before verify().
+    """
+    N = width * depth + 1
+    parents = np.zeros(N, dtype=np.int32)
+    score = np.zeros(N, dtype=np.float32)
+    mask = np.zeros((N, N), dtype=bool)
+    mask[0, 0] = True
+    first = 0
+    for step in range(depth + 1):
+        dec_len = width if step > 0 else 1
+        if step < depth:
+            logits = np.asarray(draft_logits_fn(tokens[num_nodes + first:num_nodes + first + dec_len]), dtype=np.float32)
+            ids = np.argsort(-logits, axis=-1, kind="stable")[:, :num_beams]          # topk, sorted, ties: low id first
+            top = np.take_along_axis(logits, ids, axis=-1)
+            s, t, prow = dynamic_tree_level(top, ids, score[first:first + dec_len], width)
+            new = first + dec_len
+            score[new:new + width] = s
+            tokens[num_nodes + new:num_nodes + new + width] = t
+            parents[new:new + width] = prow + first
+            mask[new:new + width] = mask[first + prow]                                  # copy the parent's row
+            mask[np.arange(new, new + width), np.arange(new, new + width)] = True       # fill_diagonal_
+        first += dec_len
+    return parents, mask, score

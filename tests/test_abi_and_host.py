@@ -1,0 +1,92 @@
+"""CPU-side checks (no GPU, no compute calls): the C-ABI library builds / loads and exports exactly the
+symbols include/umbrella_b200.h declares; the ctypes table matches the header; the host-side mirrors keep
+the reference's error behaviour; the product never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "umbrella_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(umb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from umbrella_b200 import build, _lib
+    build.build()                                       # nvcc cross-compiles without a GPU
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/umbrella_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    lib.umb_version.restype = ctypes.c_char_p
+    assert lib.umb_version().startswith(b"umbrella_b200")
+    lib.umb_awq_packed_bytes.restype = ctypes.c_size_t
+    assert lib.umb_awq_packed_bytes(8192, 8192, 128) == 64 * 64 * 8512          # 0.5195 B / parameter
+    assert lib.umb_awq_packed_bytes(8192, 8192, 64) == 0                        # unsupported group size
+
+
+def test_sass_has_tcgen05_and_tma():
+    """The GEMM really is a tensor-memory / TMA kernel (B200_PROFILING.md mnemonics)."""
+    from umbrella_b200 import _lib
+    r = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    sass = r.stdout
+    for mnemonic in ("UTCHMMA", "UBLKCP", "UTMALDG", "STTM", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_errors_mirror_the_reference():
+    from umbrella_b200.models.auto_model import AutoModelLM
+    from umbrella_b200.speculation.auto_engine import AutoEngine
+    from umbrella_b200.speculation.dynamic_speculation_engine import DynamicSpeculationEngine
+    from umbrella_b200.speculation.static_speculation_engine import StaticSpeculationEngine
+    with pytest.raises(ValueError):                      # auto_engine.py:14-16
+        AutoEngine.from_config("cuda:0", engine="nope", model="a", draft_model="b")
+    with pytest.raises(AssertionError):                  # auto_engine.py:20-21
+        AutoEngine.from_config("cuda:0", engine="static", model="a")
+    with pytest.raises(AssertionError):                  # static_speculation_engine.py:37
+        AutoEngine.from_config("cuda:0", engine="static", model="a", draft_model="b")
+    with pytest.raises(ValueError):                      # auto_model.py:166-181
+        AutoModelLM.from_pretrained("unknown/model")
+    e = AutoEngine.from_config("cuda:0", engine="dynamic", model="a", draft_model="b", width=4, depth=3, num_beams=6,
+                               generation_length=64, template="meta-llama3")
+    assert isinstance(e, DynamicSpeculationEngine) and (e.tree_width, e.tree_depth, e.num_beams) == (4, 3, 6)
+    s = AutoEngine.from_config("cuda:0", engine="static", model="a", draft_model="b", growmap_path="sequoia_tree-3x4.json")
+    assert isinstance(s, StaticSpeculationEngine)
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    import torch
+    from umbrella_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.argmax(torch.zeros(2, 8))
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "umbrella_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+
+
+def test_reference_import_paths():
+    """`umbrella` resolves to this package with the reference's module layout."""
+    import umbrella
+    from umbrella.models.auto_model import AutoModelLM                                # noqa: F401
+    from umbrella.sequoia_utils import generate_sequoia_tree                            # noqa: F401
+    from umbrella.speculation.auto_engine import AutoEngine                             # noqa: F401
+    from umbrella.speculation.dynamic_speculation_engine import DynamicSpeculationEngine  # noqa: F401
+    from umbrella.speculation.speculation_utils import (find_first_element_position, is_sentence_complete_regex,  # noqa: F401
+                                                        make_causal_mask)
+    from umbrella.speculation.static_speculation_engine import StaticSpeculationEngine  # noqa: F401
+    import umbrella_b200
+    assert umbrella.speculation.auto_engine.AutoEngine is umbrella_b200.speculation.auto_engine.AutoEngine

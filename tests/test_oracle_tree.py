@@ -204,3 +204,22 @@ def test_gather_overlap_hazard():
     c2 = ref.copy().transpose(0, 2, 1, 3).copy()           # [L, H, S, D] layout (StaticKV_Cache)
     T.kv_gather(c2, np.array([n, n + 2, n + 6]), n, seq_axis=2)
     assert (c2.transpose(0, 2, 1, 3) == cache).all()
+
+
+def test_dynamic_build_tree_matches_reference(golden_dir):
+    """The oracle's restatement of DynamicSpeculationEngine.build_tree reproduces the trees the reference
+    built on CPU (tokens, parents, mask) from the same bigram draft table, iteration by iteration."""
+    z = np.load(os.path.join(golden_dir, "accept_dynamic.npz"))
+    for ci in range(3):
+        pre = "c%d_" % ci
+        width, beams, dpt, vocab, S, n_it = map(int, z[pre + "meta"][:6])
+        N = width * dpt + 1
+        table = z[pre + "draft_table"]
+        for it in range(n_it):
+            n0 = int(z[pre + "n0"][it])
+            tokens = np.zeros(S, dtype=np.int64)
+            tokens[n0] = z[pre + "spec"][it][0]                     # the root (last accepted / bonus token)
+            parents, mask, _ = T.dynamic_build_tree(lambda ids: table[ids], tokens, n0, width, beams, dpt)
+            assert (tokens[n0:n0 + N] == z[pre + "spec"][it]).all(), (ci, it)
+            assert (parents == z[pre + "parents"][it]).all(), (ci, it)
+            assert (mask == z[pre + "tree_mask"][it].astype(bool)).all(), (ci, it)

@@ -81,9 +81,13 @@ SIGNATURES = {
     "umb_llama_gemm_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "umb_llama_forward": (c_int, [C.POINTER(LlamaModel), c_void_p, c_void_p, c_int, c_int, C.POINTER(AttnMask),
                                   c_void_p, c_int, c_void_p, c_void_p]),
+    "umb_llama_forward_range": (c_int, [C.POINTER(LlamaModel), c_void_p, c_void_p, c_int, c_int, C.POINTER(AttnMask),
+                                        c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "umb_llama_forward_dyn": (c_int, [C.POINTER(LlamaModel), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "umb_store_tokens": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "umb_dyn_tree_expand": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

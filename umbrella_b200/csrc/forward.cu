@@ -20,16 +20,20 @@ static int linear(const umb_llama_t* m, const void* x, int64_t ldx, const void* 
 // n_dev != NULL: ids / pos are base pointers, kv_offset is the row offset added to n_dev[0] on the device.
 static int forward_chunk(const umb_llama_t* m, const int64_t* ids, const int64_t* pos, int rows, int kv_offset,
                          const umb_attn_mask_t* mask, float* logits, int logits_from, unsigned long long* keys,
-                         umb_stream_t st, const int32_t* n_dev = nullptr) {
+                         umb_stream_t st, const int32_t* n_dev = nullptr, int layer_begin = 0, int layer_end = -1,
+                         bool do_embed = true) {
     const int H = m->hidden_size, I = m->intermediate_size, Hq = m->num_q_heads, Hkv = m->num_kv_heads, D = m->head_dim;
     const int qkv_n = (Hq + 2 * Hkv) * D;
     const int64_t tok_stride = (int64_t)Hkv * D;
     const int64_t layer_elems = (int64_t)m->max_length * tok_stride;
-    if (n_dev)
+    if (layer_end < 0) layer_end = m->num_layers;
+    if (!do_embed) {
+        // a later slice of a layer-by-layer (paged) forward: the hidden rows are already in m->hidden
+    } else if (n_dev)
         UMB_TRY(embedding_dyn(ids, n_dev, kv_offset, m->embed, m->hidden, rows, H, (cudaStream_t)st));
     else
         UMB_TRY(umb_embedding_f16(ids, m->embed, m->hidden, rows, H, st));
-    for (int l = 0; l < m->num_layers; ++l) {
+    for (int l = layer_begin; l < layer_end; ++l) {
         const umb_llama_layer_t& L = m->layers[l];
         __half* kc = (__half*)m->k_cache + l * layer_elems;
         __half* vc = (__half*)m->v_cache + l * layer_elems;
@@ -93,7 +97,10 @@ extern "C" int umb_llama_forward(const umb_llama_t* m, const int64_t* input_ids,
     UMB_CHECK_ARG(kv_offset + rows <= m->max_length);
     UMB_CHECK_ARG(!argmax_keys || logits);
     if (logits) UMB_CHECK_ARG(m->lm_head != nullptr);
-    const int chunk = 128;
+    // rows > 128 (prefill, dynamic trees of 257..505 nodes): equal chunks of <= 128 rows, each a full pass
+    // over the weights; later chunks see the KV rows the earlier ones appended
+    const int n_chunks = (rows + 127) / 128;
+    const int chunk = (rows + n_chunks - 1) / n_chunks;
     for (int r0 = 0; r0 < rows; r0 += chunk) {
         const int n = rows - r0 < chunk ? rows - r0 : chunk;
         umb_attn_mask_t mk = *mask;
@@ -101,8 +108,8 @@ extern "C" int umb_llama_forward(const umb_llama_t* m, const int64_t* input_ids,
             mk.dense_mask = mask->dense_mask + (int64_t)r0 * mask->mask_stride;
         } else if (mk.mask_mode == UMB_MASK_CAUSAL) {
             mk.prefix_len = mask->prefix_len + r0;
-        } else if (rows > chunk) {
-            return UMB_ERR_UNSUPPORTED;   // a token tree larger than 128 rows goes through the dense form
+        } else {
+            mk.tree_bits = mask->tree_bits + (int64_t)r0 * mask->tree_words;   // rows r0.. of the ancestor bitmask
         }
         // logits rows of this chunk
         float* lg = nullptr;
@@ -119,6 +126,21 @@ extern "C" int umb_llama_forward(const umb_llama_t* m, const int64_t* input_ids,
         if (rc != UMB_OK) return rc;
     }
     return UMB_OK;
+}
+
+extern "C" int umb_llama_forward_range(const umb_llama_t* m, const int64_t* input_ids, const int64_t* position_ids,
+                                       int rows, int kv_offset, const umb_attn_mask_t* mask, int layer_begin,
+                                       int layer_end, int do_embed, float* logits, int logits_from_row,
+                                       unsigned long long* argmax_keys, umb_stream_t stream) {
+    UMB_CHECK_ARG(m && input_ids && position_ids && mask && rows >= 1 && rows <= 128 && kv_offset >= 0);
+    UMB_CHECK_ARG(m->layers && m->embed && m->final_norm && m->cos && m->sin && m->k_cache && m->v_cache);
+    UMB_CHECK_ARG(m->hidden && m->normed && m->qkv && m->q_rot && m->attn_out && m->act && m->gemm_ws);
+    UMB_CHECK_ARG(kv_offset + rows <= m->max_length);
+    UMB_CHECK_ARG(layer_begin >= 0 && layer_begin <= layer_end && layer_end <= m->num_layers);
+    UMB_CHECK_ARG(!argmax_keys || logits);
+    if (logits) UMB_CHECK_ARG(m->lm_head != nullptr && logits_from_row >= 0 && logits_from_row < rows);
+    return umb::forward_chunk(m, input_ids, position_ids, rows, kv_offset, mask, logits, logits_from_row, argmax_keys,
+                              stream, nullptr, layer_begin, layer_end, do_embed != 0);
 }
 
 extern "C" int umb_llama_forward_dyn(const umb_llama_t* m, const int64_t* tokens_base, const int64_t* position_base,

@@ -192,3 +192,91 @@ extern "C" int umb_store_tokens(int64_t* tokens_base, const int32_t* n_dev, int 
     umb::count_launches(1);
     return UMB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Dynamic (SpecExec-style) tree growth: one level of DynamicSpeculationEngine.build_tree
+// (reference umbrella/speculation/dynamic_speculation_engine.py:231-248) in one CTA.
+//   cand[r, b]  = tree_score[level_first + r] + log(softmax(topk_logits[r, :])[b] + 1e-4)
+//                 (softmax over the top-`beams` slice only, dynamic...:236-237)
+//   the `width` best candidates, best first (torch.topk order; equal scores: lower flat index first)
+//   become the next level: node id = level_first + rows + j
+//   tree_score[id] = score, tokens[n + id] = topk_ids[flat], parents[id] = level_first + flat / beams,
+//   tree_bits[id, :] = tree_bits[parent, :] | bit id   (the reference copies the parent's mask row and
+//   sets the diagonal, dynamic...:247-248)
+// ------------------------------------------------------------------------------------------------
+namespace umb {
+constexpr int kExpandThreads = 512;
+constexpr int kMaxCand = 4096;
+
+__global__ void __launch_bounds__(kExpandThreads, 1)
+dyn_tree_expand_kernel(const float* __restrict__ topk_logits, const int64_t* __restrict__ topk_ids, int rows, int beams,
+                       int width, int level_first, int num_nodes_host, const int32_t* __restrict__ n_dev,
+                       float* __restrict__ tree_score, int64_t* __restrict__ tokens, int32_t* __restrict__ parents,
+                       uint32_t* __restrict__ tree_bits, int tree_words) {
+    __shared__ float s_cand[kMaxCand];
+    __shared__ float s_row_max[128], s_row_sum[128];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int n = n_dev ? n_dev[0] : num_nodes_host;
+    const int total = rows * beams;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kExpandThreads / 32;
+    // per-row max and sum(exp(x - max)) (torch softmax: fp32, max-subtracted)
+    for (int r = warp; r < rows; r += nwarps) {
+        float mx = -INFINITY;
+        for (int b = lane; b < beams; b += 32) mx = fmaxf(mx, topk_logits[r * beams + b]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int b = lane; b < beams; b += 32) sum += expf(topk_logits[r * beams + b] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+            s_row_max[r] = mx;
+            s_row_sum[r] = sum;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < total; c += kExpandThreads) {
+        const int r = c / beams;
+        const float pr = expf(topk_logits[c] - s_row_max[r]) / s_row_sum[r];
+        s_cand[c] = tree_score[level_first + r] + logf(pr + 1e-4f);
+    }
+    __syncthreads();
+    // rank by counting: candidate c lands at output position #(better candidates)
+    for (int c = threadIdx.x; c < total; c += kExpandThreads) {
+        const float v = s_cand[c];
+        int rank = 0;
+        for (int j = 0; j < total; ++j) {
+            const float o = s_cand[j];
+            rank += (o > v) || (o == v && j < c);
+        }
+        if (rank < width) {
+            const int id = level_first + rows + rank;
+            const int par = level_first + c / beams;
+            tree_score[id] = v;
+            tokens[(int64_t)n + id] = topk_ids[c];
+            parents[id] = par;
+            for (int w = 0; w < tree_words; ++w) {
+                uint32_t bits = tree_bits[(int64_t)par * tree_words + w];
+                if (w == (id >> 5)) bits |= 1u << (id & 31);
+                tree_bits[(int64_t)id * tree_words + w] = bits;
+            }
+        }
+    }
+}
+}  // namespace umb
+
+extern "C" int umb_dyn_tree_expand(const float* topk_logits, const int64_t* topk_ids, int rows, int beams, int width,
+                                   int level_first, int num_nodes, const int32_t* n_dev, float* tree_score,
+                                   int64_t* tokens, int32_t* parents, uint32_t* tree_bits, int tree_words,
+                                   umb_stream_t stream) {
+    UMB_CHECK_ARG(topk_logits && topk_ids && tree_score && tokens && parents && tree_bits);
+    UMB_CHECK_ARG(rows >= 1 && rows <= 128 && beams >= 1 && width >= 1 && level_first >= 0 && num_nodes >= 0);
+    UMB_CHECK_ARG(width <= rows * beams && tree_words >= 1 && (level_first + rows + width) <= tree_words * 32);
+    if (rows * beams > umb::kMaxCand) return UMB_ERR_UNSUPPORTED;
+    UMB_LAUNCH_PDL(umb::dyn_tree_expand_kernel, dim3(1), dim3(umb::kExpandThreads), 0, (cudaStream_t)stream, topk_logits,
+                   topk_ids, rows, beams, width, level_first, num_nodes, n_dev, tree_score, tokens, parents, tree_bits,
+                   tree_words);
+    umb::count_launches(1);
+    return UMB_OK;
+}

@@ -20,14 +20,25 @@ class _NamedLlama:
         raise TypeError("factory only")
 
 
-def _make(model_name, batch_size=1, max_length=256, device="cuda:0", dtype=torch.float16, **unused):
+def _weight_bytes(shape, awq: bool) -> int:
+    per_layer = sum(k * n for k, n in L.linear_dims(shape).values())
+    body = shape.num_hidden_layers * per_layer * (0.5 + 2.5 / shape.group_size if awq else 2)
+    head = shape.vocab_size * shape.hidden_size * 2 * (1 if shape.tie_word_embeddings else 2)
+    return int(body + head)
+
+
+def _make(model_name, offload=False, batch_size=1, max_length=256, device="cuda:0", dtype=torch.float16, **unused):
     entry = L.KNOWN_MODELS.get(model_name)
     if entry is None:
         raise ValueError(f"Model type '{model_name}' is not supported. "
                          f"Supported types: {[k for k, v in L.KNOWN_MODELS.items() if v]}")
     shape, awq = entry
-    model = (L.LlamaAwq if awq else L.Llama)(shape, max_length=max_length, device=device, dtype=dtype,
-                                             batch_size=batch_size, model_name=model_name)
+    if offload:
+        from .offload import LlamaAwqOffload, LlamaOffload
+        cls = LlamaAwqOffload if awq else LlamaOffload
+    else:
+        cls = L.LlamaAwq if awq else L.Llama
+    model = cls(shape, max_length=max_length, device=device, dtype=dtype, batch_size=batch_size, model_name=model_name)
     base_alloc = model.alloc
 
     def alloc(**kwargs):
@@ -37,7 +48,16 @@ def _make(model_name, batch_size=1, max_length=256, device="cuda:0", dtype=torch
         gen_device = kwargs.get("synthetic_gen_device", str(model.device))
         if exit_layer is not None and not awq and 0 < exit_layer < model.num_layers:
             model.num_layers = exit_layer              # draft truncation (llama.py:421,450-451)
-        base_alloc()
+        if offload:
+            # The reference pages whatever ``num_cache_layers`` leaves out (configs written for 12-48 GB
+            # cards).  On a 180 GB B200 a model that fits stays fully resident unless ``force_offload`` asks
+            # for the paged path; a model that does not fit pages exactly as configured.
+            free, _ = torch.cuda.mem_get_info(model.device)
+            if not kwargs.get("force_offload", False) and _weight_bytes(shape, awq) < 0.8 * free:
+                kwargs = dict(kwargs, num_cache_layers=model.num_layers)
+            base_alloc(**kwargs)
+        else:
+            base_alloc()
         head = L.synth_head(shape, seed, gen_device)
         model.load_head(head["embed_tokens"], head["lm_head"], head["norm"])
         for i in range(model.num_layers):
@@ -59,7 +79,7 @@ class AutoModelLM:
         if model_name not in cls._MODEL_MAPPING:
             raise ValueError(f"Model type '{model_name}' is not supported. "
                              f"Supported types: {list(cls._MODEL_MAPPING.keys())}")
-        # offload / cuda_graph select host-paging and graph-replay variants in the reference; on a
-        # 180 GB B200 every configured model is resident, and the native forward replaces per-op
-        # Python, so both map to the same resident model here.
-        return _make(model_name, **kwargs)
+        # offload=True -> the paged classes of models/offload.py (LlamaOffload / LlamaAwqOffload);
+        # cuda_graph selects a graph-replay variant in the reference -- here the engines capture the
+        # whole iteration themselves over the same native forward.
+        return _make(model_name, offload=offload, **kwargs)

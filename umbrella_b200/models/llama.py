@@ -372,10 +372,17 @@ def synth_head(shape: LlamaShape, seed: int, gen_device="cpu") -> dict:
 
 
 def SyntheticLlama(shape: LlamaShape, max_length: int, awq: bool, seed: int = 1234, device: str = "cuda:0",
-                   num_layers: int | None = None, gen_device: str = "cpu"):
-    """A ready-to-run model with seeded synthetic weights of the given architecture."""
-    model = (LlamaAwq if awq else Llama)(shape, max_length=max_length, device=device, num_layers=num_layers)
-    model.alloc()
+                   num_layers: int | None = None, gen_device: str = "cpu", offload: dict | None = None):
+    """A ready-to-run model with seeded synthetic weights of the given architecture.  ``offload`` (e.g.
+    ``{"num_cache_layers": 0}``) builds the paged variant of models/offload.py with those alloc kwargs."""
+    if offload is not None:
+        from .offload import LlamaAwqOffload, LlamaOffload
+        model = (LlamaAwqOffload if awq else LlamaOffload)(shape, max_length=max_length, device=device,
+                                                           num_layers=num_layers)
+        model.alloc(**offload)
+    else:
+        model = (LlamaAwq if awq else Llama)(shape, max_length=max_length, device=device, num_layers=num_layers)
+        model.alloc()
     head = synth_head(shape, seed, gen_device)
     model.load_head(head["embed_tokens"], head["lm_head"], head["norm"])
     for i in range(model.num_layers):

@@ -217,6 +217,22 @@ def store_tokens(tokens: torch.Tensor, n_dev: torch.Tensor, offset: int, src: to
     check(_lib.load().umb_store_tokens(_p(tokens), _p(n_dev), offset, _p(src), src.numel(), _stream()), "store_tokens")
 
 
+def dyn_tree_expand(topk_logits: torch.Tensor, topk_ids: torch.Tensor, width: int, level_first: int, num_nodes: int,
+                    tree_score: torch.Tensor, tokens: torch.Tensor, parents: torch.Tensor, tree_bits: torch.Tensor,
+                    n_dev: torch.Tensor | None = None):
+    """One level of the dynamic tree builder (dynamic_speculation_engine.py:231-248): beam scores ->
+    the ``width`` best children, their tokens, parents, scores and ancestor-bit rows."""
+    _cuda(topk_logits, torch.float32, "topk_logits"), _cuda(topk_ids, torch.int64, "topk_ids")
+    _cuda(tree_score, torch.float32, "tree_score"), _cuda(tokens, torch.int64, "tokens")
+    _cuda(parents, torch.int32, "parents")
+    assert tree_bits.dtype in (torch.int32, torch.uint32) and tree_bits.is_contiguous()
+    assert topk_logits.is_contiguous() and topk_ids.is_contiguous() and topk_logits.shape == topk_ids.shape
+    rows, beams = topk_logits.shape
+    check(_lib.load().umb_dyn_tree_expand(_p(topk_logits), _p(topk_ids), rows, beams, width, level_first, num_nodes,
+                                          _p(n_dev), _p(tree_score), _p(tokens), _p(parents), _p(tree_bits),
+                                          tree_bits.shape[1], _stream()), "dyn_tree_expand")
+
+
 def kv_gather(k_cache: torch.Tensor, v_cache: torch.Tensor, result: torch.Tensor, offset: int, layout: str = "LSHD",
               zero_upto: int = 0, offset_dev: torch.Tensor | None = None):
     """In-place compaction of accepted rows for every layer.  k/v: [L, S, Hkv, D] ("LSHD", KV_Cache)

@@ -1,11 +1,10 @@
 """AutoEngine.from_config (mirror of reference umbrella/speculation/auto_engine.py:4-22)."""
+from .dynamic_speculation_engine import DynamicSpeculationEngine
 from .static_speculation_engine import StaticSpeculationEngine
 
 
 class AutoEngine:
-    # The dynamic (SpecExec-style) engine's draft-side tree builder is a "next" row of SURVEY.md 8f;
-    # its verify/accept/gather path is the same kernels as the static engine's.
-    _ENGINE_MAPPING = {"static": StaticSpeculationEngine}
+    _ENGINE_MAPPING = {"static": StaticSpeculationEngine, "dynamic": DynamicSpeculationEngine}
 
     @classmethod
     def from_config(cls, device: str, **kwargs):
