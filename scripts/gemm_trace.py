@@ -1,6 +1,7 @@
 """Per-CTA timeline of one GEMM launch (UMB_GEMM_TRACE=1): where the fixed per-launch time goes."""
 import ctypes as C, os, sys
 os.environ["UMB_GEMM_TRACE"] = "1"
+os.environ.setdefault("UMB_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "umbrella_b200", "libumbrella_b200.trace.so"))  # python -m umbrella_b200.build --variant trace -DUMB_GEMM_TRACE_BUILD=1
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from umbrella_b200 import ops, _lib

@@ -48,6 +48,20 @@ constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each,
 constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1);   // producer + 2 MMA issuers + dequant groups + epilogue group (AWQ)
 constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
+// Experiment switches (variant builds, scripts/sweep_variants.sh).  Measured on B200 at M = 13, 70B shapes
+// (profiles/r1_gemm_experiments.txt), sum of the four GEMMs of a layer:
+//   defaults below 129.7 us | UMB_EARLY_W=4 131.0 | + UMB_SLEEP_WAIT=3 131.2 | + UMB_DQ_PIPELINE=1 135.9
+// i.e. none of them pays: the steady state is bound by the fp16x2 / lop3 issue rate of the dequant warps
+// (0.5 warp-instructions per cycle per scheduler for HFMA2/HMUL2/HADD2/LOP3, scripts/ubench/pipe_rates.cu).
+#ifndef UMB_DQ_PIPELINE
+#define UMB_DQ_PIPELINE 0      // 1: fetch the next unit's packed words under the tcgen05.st of the current one
+#endif
+#ifndef UMB_SLEEP_WAIT
+#define UMB_SLEEP_WAIT 0       // bit 0: producer, bit 1: epilogue warps sleep between mbarrier polls
+#endif
+#ifndef UMB_EARLY_W
+#define UMB_EARLY_W 16         // weight records requested before griddepcontrol.wait (>= ring depth: all)
+#endif
 
 // nibble position of the i-th of 8 consecutive values inside a 32-bit word: (0,4,1,5,2,6,3,7).
 // Used by the AutoAWQ checkpoint layout (along N) and by our repacked stream (along K): nibbles p
@@ -173,6 +187,15 @@ __device__ __forceinline__ void dequant_word(uint32_t w, uint32_t magic, __half2
                                              uint32_t* out) {
     const __half2 sixteenth = as_h2(0x2C002C00u);                 // 1/16
     const uint32_t w8 = w >> 8;
+#ifdef UMB_EXPERIMENT_ONE_FMA
+    // timing experiment only (numerically wrong): one half2 op per nibble pair instead of two
+    out[0] = as_u32(__hfma2(as_h2(lop3_and_or<0x000f000fu>(w, magic)), s2, neg_co));
+    out[1] = as_u32(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w, magic)), s2, neg_co));
+    out[2] = as_u32(__hfma2(as_h2(lop3_and_or<0x000f000fu>(w8, magic)), s2, neg_co));
+    out[3] = as_u32(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w8, magic)), s2, neg_co));
+    (void)ce; (void)sixteenth;
+    return;
+#endif
     // (t - ce) and fma(t, 1/16, -co) are exact; the multiply by the scale is the single rounding
     out[0] = as_u32(__hmul2(__hsub2(as_h2(lop3_and_or<0x000f000fu>(w, magic)), ce), s2));
     out[1] = as_u32(__hmul2(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w, magic)), sixteenth, neg_co), s2));
@@ -218,7 +241,13 @@ __device__ __forceinline__ unsigned long long gtimer() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) : : "memory");
     return t;
 }
+// The timeline stamps are compiled in only for the `trace` variant build (-DUMB_GEMM_TRACE_BUILD=1,
+// scripts/gemm_trace.py): even a predicated-off stamp costs issue slots inside the dequant loop.
+#ifdef UMB_GEMM_TRACE_BUILD
 #define UMB_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+#else
+#define UMB_TRACE(slot) do { } while (0)
+#endif
 
 template <int MPAD>
 struct GemmCfg {
@@ -413,63 +442,72 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
         const unsigned char* src = p.packed + (kAwq ? u_begin * kRecordStride : 0);
         const int n_pre = n_units < kStages ? n_units : kStages;
+        // Only the first kEarlyW weight records are requested before griddepcontrol.wait: the copy engine
+        // serves its queue in order, so x slabs issued behind a full ring of weight copies would reach shared
+        // memory (and let the first MMA start) only after ~85 KB per SM had streamed in.
+        constexpr int kEarlyW = UMB_EARLY_W;
+        const int n_early = n_pre < kEarlyW ? n_pre : kEarlyW;
         int tile = tile0, g = in_tile0;                          // (tile, g) of the next weight copy
-        for (int i = 0; i < n_pre; ++i) {                        // weights first: independent of the predecessor
-            if (elect_one()) {
-                mbar_arrive_expect_tx(full_w + i, kWTxBytes);
-                if constexpr (kAwq)
-                    tma_bulk_g2s(s_w + i * kWStride, src, kRecordBytes, full_w + i, pol_w);
-                else
-                    tma_tensor2d_g2s(s_w + i * kWStride, &tmap_w, g * 64, tile * kTileN, full_w + i, pol_w);
+        auto issue_w = [&](int stage) {
+            mbar_arrive_expect_tx(full_w + stage, kWTxBytes);
+            if constexpr (kAwq)
+                tma_bulk_g2s(s_w + stage * kWStride, src, kRecordBytes, full_w + stage, pol_w);
+            else
+                tma_tensor2d_g2s(s_w + stage * kWStride, &tmap_w, g * 64, tile * kTileN, full_w + stage, pol_w);
+        };
+        auto issue_x = [&](int stage, int gk) {
+            mbar_arrive_expect_tx(full_x + stage, (uint32_t)kXBytes);
+            unsigned char* xs = s_x + stage * kXBytes;
+            if constexpr (kAwq) {
+                tma_tensor2d_g2s(xs, &tmap_x, gk * kGroup, 0, full_x + stage, pol_x);
+                tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, gk * kGroup + 64, 0, full_x + stage, pol_x);
+            } else {
+                tma_tensor2d_g2s(xs, &tmap_x, gk * 64, 0, full_x + stage, pol_x);
             }
-            __syncwarp();
+        };
+        auto advance_w = [&]() {
             src += kRecordStride;
             if (++g == p.units_per_tile) {
                 g = 0;
                 ++tile;
             }
+        };
+        for (int i = 0; i < n_early; ++i) {                      // weights first: independent of the predecessor
+            if (elect_one()) issue_w(i);
+            __syncwarp();
+            advance_w();
         }
         if (lane == 0) UMB_TRACE(2);
         pdl_wait();                                              // x is the predecessor's output
         if (lane == 0) UMB_TRACE(3);
         int gx = in_tile0;
-        for (int i = 0; i < n_pre; ++i) {
-            if (elect_one()) {
-                mbar_arrive_expect_tx(full_x + i, (uint32_t)kXBytes);
-                unsigned char* xs = s_x + i * kXBytes;
-                if constexpr (kAwq) {
-                    tma_tensor2d_g2s(xs, &tmap_x, gx * kGroup, 0, full_x + i, pol_x);
-                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, gx * kGroup + 64, 0, full_x + i, pol_x);
-                } else {
-                    tma_tensor2d_g2s(xs, &tmap_x, gx * 64, 0, full_x + i, pol_x);
-                }
-            }
+        for (int i = 0; i < n_early; ++i) {
+            if (elect_one()) issue_x(i, gx);
             __syncwarp();
             if (++gx == p.units_per_tile) gx = 0;
+        }
+        for (int i = n_early; i < n_pre; ++i) {                  // rest of the ring: stages still untouched
+            if (elect_one()) {
+                issue_w(i);
+                issue_x(i, g);
+            }
+            __syncwarp();
+            advance_w();
         }
         Ring r;
         r.phase = 1;                                             // every stage has been used once
         for (int i = n_pre; i < n_units; ++i) {
-            mbar_wait(done + r.stage, r.phase ^ 1);              // the unit that last used this stage has retired
+#if UMB_SLEEP_WAIT & 1
+            mbar_wait_sleep<32>(done + r.stage, r.phase ^ 1);    // the unit that last used this stage has retired
+#else
+            mbar_wait(done + r.stage, r.phase ^ 1);
+#endif
             if (elect_one()) {
-                mbar_arrive_expect_tx(full_w + r.stage, kWTxBytes);
-                mbar_arrive_expect_tx(full_x + r.stage, (uint32_t)kXBytes);
-                unsigned char* xs = s_x + r.stage * kXBytes;
-                if constexpr (kAwq) {
-                    tma_bulk_g2s(s_w + r.stage * kWStride, src, kRecordBytes, full_w + r.stage, pol_w);
-                    tma_tensor2d_g2s(xs, &tmap_x, g * kGroup, 0, full_x + r.stage, pol_x);
-                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full_x + r.stage, pol_x);
-                } else {
-                    tma_tensor2d_g2s(s_w + r.stage * kWStride, &tmap_w, g * 64, tile * kTileN, full_w + r.stage, pol_w);
-                    tma_tensor2d_g2s(xs, &tmap_x, g * 64, 0, full_x + r.stage, pol_x);
-                }
+                issue_w(r.stage);
+                issue_x(r.stage, g);
             }
             __syncwarp();
-            src += kRecordStride;
-            if (++g == p.units_per_tile) {
-                g = 0;
-                ++tile;
-            }
+            advance_w();
             r.advance(kStages);
         }
         if (lane == 0) UMB_TRACE(10);
@@ -557,8 +595,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 int w_first = grp;                                                 // first unit of this group that re-uses a TMEM stage
                 while (w_first < kAStages) w_first += kDqGroups;
                 int w_st = (w_first - kAStages) % kStages, w_ph = 0;               // ring position of unit `mine - kAStages`
+                // Software pipeline: the packed words / scale / zero of this group's NEXT unit are pulled into
+                // registers while the tcgen05.st of the current unit drains, so the shared-memory latency and
+                // the barrier poll of one unit hide behind the tensor-memory stores of the previous one.
+                uint4 w4[4];
+                uint32_t sbits = 0, zw = 0;
+                auto fetch = [&](int st_) {
+                    const uint32_t rec = smem_u32(s_w + st_ * kWStride);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) w4[c] = lds128(rec + (c * kTileN + fl) * 16);    // 128 k of this feature row
+                    sbits = lds16(rec + kRecScaleOff + fl * 2);
+                    zw = lds32(rec + kRecZeroOff + (fl >> 3) * 4);
+                };
+                if (grp < n_units) {
+                    mbar_wait(full_w + dq_st, dq_ph);
+                    if (grp == 0 && q == 0 && lane == 0) UMB_TRACE(4);
+                    fetch(dq_st);
+                }
                 for (int mine = grp; mine < n_units; mine += kDqGroups) {
-                    const int st = dq_st, ph = dq_ph, ts = dq_ts;
+                    const int ts = dq_ts;
                     dq_st += kDqGroups;
                     if (dq_st >= kStages) {
                         dq_st -= kStages;
@@ -566,14 +621,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     }
                     dq_ts += kDqGroups;
                     if (dq_ts >= kAStages) dq_ts -= kAStages;
-                    mbar_wait(full_w + st, ph);
-                    if (mine == 0 && q == 0 && lane == 0) UMB_TRACE(4);
-                    const uint32_t rec = smem_u32(s_w + st * kWStride);
-                    uint4 w4[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) w4[c] = lds128(rec + (c * kTileN + fl) * 16);    // 128 k of this feature row
-                    const uint32_t sbits = lds16(rec + kRecScaleOff + fl * 2);
-                    const uint32_t zw = lds32(rec + kRecZeroOff + (fl >> 3) * 4);
                     const uint32_t z = (zw >> (4 * (fl & 7))) & 0xFu;
                     const __half2 ce = as_h2((0x6400u | z) * 0x10001u);                 // (1024 + z) x2
                     const __half2 neg_co = as_h2((0xD400u | (z << 4)) * 0x10001u);      // -(64 + z) x2
@@ -598,10 +645,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         }
                         UMB_TMEM_ST_X16(taddr + c * 16, a);
                     }
+                    const bool more = mine + kDqGroups < n_units;
+                    // next record already in shared memory? then read it under the stores (warp-uniform answer)
+#if UMB_DQ_PIPELINE
+                    const bool early = more && __shfl_sync(0xffffffffu, (int)mbar_try_wait(full_w + dq_st, dq_ph), 0) != 0;
+#else
+                    const bool early = false;
+#endif
+                    if (early) fetch(dq_st);
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full + ts);
+                    if (more && !early) {
+                        mbar_wait(full_w + dq_st, dq_ph);
+                        fetch(dq_st);
+                    }
                 }
             }
         } else {
@@ -617,7 +676,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 // which MMA warps issued into their accumulators during this segment
                 const int n_odd = (seg_end >> 1) - (seg_begin >> 1);               // odd CTA-local indices in [begin, end)
                 const int use_mask = ((seg_len - n_odd) > 0 ? 1 : 0) | (n_odd > 0 ? 2 : 0);
+#if UMB_SLEEP_WAIT & 2
+                mbar_wait_sleep<64>(acc_full, seg & 1);          // a whole segment away: do not spin on issue slots
+#else
                 mbar_wait(acc_full, seg & 1);
+#endif
                 tc_fence_after();
                 if (ew == 0 && lane == 0) UMB_TRACE(seg == 0 ? 7 : 12);
                 if (whole) {

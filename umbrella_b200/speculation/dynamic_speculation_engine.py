@@ -90,7 +90,6 @@ class DynamicSpeculationEngine(BaseEngine):
         self._argmax_keys = torch.zeros(N, dtype=torch.int64, device=dev)
         self._result = torch.zeros(4 + N, dtype=torch.int32, device=dev)
         self._result_host = torch.zeros(4 + N, dtype=torch.int32).pin_memory()
-        self._state = torch.zeros(4, dtype=torch.int32, device=dev)
         self._set_eos(list(self.target_model.eos_tokens))
 
     def _set_eos(self, eos_tokens):
@@ -198,7 +197,7 @@ class DynamicSpeculationEngine(BaseEngine):
             sampled = self.acceptance_script(self, sampled)
         self.last_sampled = sampled
         ops.tree_accept(sampled, self.tokens[0], self.position_ids[0], self.parents, self.depth32, n, self._eos_dev,
-                        self._result, state=self._state)
+                        self._result)
         self.draft_model.kv_cache.gather_from_result(self._result, n, 0)
         self.target_model.kv_cache.gather_from_result(self._result, n, 0)
         self._result_host.copy_(self._result, non_blocking=True)
