@@ -35,6 +35,16 @@ GEN_LEN = 256
 MAX_LENGTH = 2048
 
 
+def _ncu_traffic():
+    """DRAM bytes per AWQ GEMM launch from the committed ncu --set full capture (scripts/ncu_traffic.py);
+    None when the capture is absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        return float(t["awq_gemm_traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def _peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -208,7 +218,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "gemm_kernel<16,true> (AWQ INT4 dequant + tcgen05 GEMM), 320 launches per verify",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": _ncu_traffic(),
+                         "traffic_source": "profiles/r1_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                           "ncu --set full, mean of the 4 GEMM shapes of a layer",
                          "algorithmic_bytes_per_launch": awq_bytes / 320, "avg_launch_us": awq_ms * 1e3 / 320},
             "verify_pass": {"ms": verify_ms, "algorithmic_bytes": wbytes + kv_bytes,
                             "hbm_frac": (wbytes + kv_bytes) / (verify_ms * 1e-3) / 1e9 / peak},

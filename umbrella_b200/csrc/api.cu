@@ -1,5 +1,6 @@
 // Library bookkeeping: version, error strings, launch counter, device properties.
 #include <atomic>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -15,6 +16,15 @@ bool pdl_enabled() {
         cached = (e && e[0] == '0') ? 0 : 1;
     }
     return cached != 0;
+}
+int arg_fail(const char* file, int line, const char* what) {
+    static int dbg = -1;
+    if (dbg < 0) {
+        const char* e = getenv("UMB_DEBUG");
+        dbg = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (dbg) fprintf(stderr, "umbrella_b200: argument check failed at %s:%d: %s\n", file, line, what);
+    return UMB_ERR_ARG;
 }
 int sm_count() {
     static int cached = 0;

@@ -9,7 +9,8 @@
 
 #include "../../include/umbrella_b200.h"
 
-#define UMB_CHECK_ARG(cond) do { if (!(cond)) return UMB_ERR_ARG; } while (0)
+namespace umb { int arg_fail(const char* file, int line, const char* what); }   // api.cu: UMB_DEBUG=1 prints the check
+#define UMB_CHECK_ARG(cond) do { if (!(cond)) return umb::arg_fail(__FILE__, __LINE__, #cond); } while (0)
 #define UMB_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
 #define UMB_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
 

@@ -59,6 +59,13 @@ constexpr int kTmemCols = 512;
 #ifndef UMB_SLEEP_WAIT
 #define UMB_SLEEP_WAIT 0       // bit 0: producer, bit 1: epilogue warps sleep between mbarrier polls
 #endif
+#ifndef UMB_EARLY_REDUCE
+#define UMB_EARLY_REDUCE 0     // 1: epilogue warps fetch residual rows / other CTAs' partials before their own
+                               // accumulators (measured: 130.2 us vs 126.4 us per layer without -- left off)
+#endif
+#ifndef UMB_EARLY_W_F16
+#define UMB_EARLY_W_F16 2      // same, fp16-weight GEMMs
+#endif
 #ifndef UMB_EARLY_W
 #define UMB_EARLY_W 16         // weight records requested before griddepcontrol.wait (>= ring depth: all)
 #endif
@@ -280,7 +287,7 @@ __device__ __forceinline__ unsigned int orderable_f32_g(float f) {
 // Epilogue of 16 token columns [m0, m0 + 16) for feature lane `fl` (0..127) of tile `tile`.
 template <int MPAD>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, int fl, int m0, const float (&v)[16],
-                                               __half* exch) {
+                                               __half* exch, const __half* res_pre = nullptr) {
     const int n = tile * kTileN + fl;
     if (p.mode == UMB_EPI_SILU_MUL) {
         // lanes 64..127 hold `up`, lanes 0..63 hold `gate` of output feature tile*64 + (fl & 63)
@@ -314,9 +321,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
     // store of the previous row would be serialised behind it (one L2 round trip per token row)
     __half res[16];
     if (p.mode == UMB_EPI_RESIDUAL) {
+        if (res_pre) {                                // loaded while the MMAs of this segment were still running
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < mcols) res[j] = p.residual[(int64_t)(m0 + j) * p.ld_residual + n];
+            for (int j = 0; j < 16; ++j) res[j] = res_pre[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < mcols) res[j] = p.residual[(int64_t)(m0 + j) * p.ld_residual + n];
+        }
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -445,7 +457,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         // Only the first kEarlyW weight records are requested before griddepcontrol.wait: the copy engine
         // serves its queue in order, so x slabs issued behind a full ring of weight copies would reach shared
         // memory (and let the first MMA start) only after ~85 KB per SM had streamed in.
-        constexpr int kEarlyW = UMB_EARLY_W;
+        // (AWQ: the dequant warps, not the MMAs, set the pace, and prefetching the whole ring under the
+        // predecessor's tail measured slightly better -- UMB_EARLY_W = 16.  fp16 weights (draft model, lm_head):
+        // nothing happens between "landed" and "MMA", so the first x slab must not wait behind the ring.)
+        constexpr int kEarlyW = kAwq ? UMB_EARLY_W : UMB_EARLY_W_F16;
         const int n_early = n_pre < kEarlyW ? n_pre : kEarlyW;
         int tile = tile0, g = in_tile0;                          // (tile, g) of the next weight copy
         auto issue_w = [&](int stage) {
@@ -669,6 +684,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             pdl_wait();                                  // residual / workspace / y belong to the predecessors
             if (ew == 0 && lane == 0) UMB_TRACE(11);
             int seg = 0, seg_begin = 0, in_tile = in_tile0, tile = tile0;
+            // acc[j] += the partial sums the other CTAs of `tile_` published for token columns [m0, m0 + 16), in
+            // ascending CTA order (deterministic); the polled words are stored back as zeros.
+            auto reduce_others = [&](float (&acc)[16], int m0, int tile_, int c_first, int n_other) {
+                const int mcols = p.M - m0;
+                uint32_t* sl0 = reinterpret_cast<uint32_t*>(p.slots) +
+                                ((size_t)tile_ + c_first + 1) * (MPAD * kTileN) + m0 * kTileN + fl;
+                if (mcols <= 4) {
+                    // few token rows (draft levels): 8 slots in flight per round trip
+                    for (int c0 = 0; c0 < n_other; c0 += 8) {
+                        uint32_t t[8][4];
+                        bool pending;
+                        do {
+                            pending = false;
+#pragma unroll
+                            for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const bool need = c0 + cc < n_other && j < mcols;
+                                    t[cc][j] = need ? ld_relaxed_gpu_u32(sl0 + (size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN) : 0x80000000u;
+                                }
+#pragma unroll
+                            for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) pending |= t[cc][j] == 0u;
+                        } while (pending);
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                acc[j] += __uint_as_float(t[cc][j]);
+                                if (c0 + cc < n_other && j < mcols) sl0[(size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN] = 0u;
+                            }
+                    }
+                } else if (mcols > 0) {
+                    for (int c0 = 0; c0 < n_other; c0 += 2) {
+                        uint32_t t[2][16];
+                        bool pending;
+                        do {
+                            pending = false;
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const bool need = c0 + cc < n_other && j < mcols;
+                                    t[cc][j] = need ? ld_relaxed_gpu_u32(sl0 + (size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN) : 0x80000000u;
+                                }
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) pending |= t[cc][j] == 0u;
+                        } while (pending);
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                acc[j] += __uint_as_float(t[cc][j]);
+                                if (c0 + cc < n_other && j < mcols) sl0[(size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN] = 0u;
+                            }
+                    }
+                }
+            };
             while (seg_begin < n_units) {
                 const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
                 const int seg_len = seg_end - seg_begin;
@@ -676,6 +752,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 // which MMA warps issued into their accumulators during this segment
                 const int n_odd = (seg_end >> 1) - (seg_begin >> 1);               // odd CTA-local indices in [begin, end)
                 const int use_mask = ((seg_len - n_odd) > 0 ? 1 : 0) | (n_odd > 0 ? 2 : 0);
+                const long long tile_u0 = (long long)tile * p.units_per_tile;
+                const int c_first = whole ? (int)blockIdx.x : sk_owner(tile_u0, U, P);
+                const int c_last = whole ? (int)blockIdx.x : sk_owner(tile_u0 + p.units_per_tile - 1, U, P);
+                const bool reducer = !whole && (int)blockIdx.x == c_first;
+                // Work that does not depend on this segment's own accumulators is done BEFORE waiting for them
+                // (MPAD = 16: one 16-column chunk): the residual rows are fetched and, on the reducing CTA, the
+                // other CTAs' partial sums (published early: they are the first segment of their owners) are
+                // pre-added -- two L2 round trips that otherwise sit on the tail of every launch.
+                float pre[16];
+                __half res_pre[16];
+                bool have_pre = false, have_res = false;
+                if constexpr (MPAD == 16 && UMB_EARLY_REDUCE) {
+                    if ((whole || reducer) && p.mode == UMB_EPI_RESIDUAL && tile * kTileN + fl < p.N_total) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < p.M) res_pre[j] = p.residual[(int64_t)j * p.ld_residual + tile * kTileN + fl];
+                        have_res = true;
+                    }
+                    if (reducer) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pre[j] = 0.f;
+                        reduce_others(pre, 0, tile, c_first, c_last - c_first);
+                        have_pre = true;
+                    }
+                }
 #if UMB_SLEEP_WAIT & 2
                 mbar_wait_sleep<64>(acc_full, seg & 1);          // a whole segment away: do not spin on issue slots
 #else
@@ -693,7 +794,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                             __syncwarp();
                             if (lane == 0) mbar_arrive(acc_empty);
                         }
-                        if (m0 < p.M || p.mode == UMB_EPI_SILU_MUL) epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
+                        if (m0 < p.M || p.mode == UMB_EPI_SILU_MUL)
+                            epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch, have_res ? res_pre : nullptr);
                     }
                 } else {
                     // Partial tile.  The CTA that owns the HEAD of the tile (c_first; that part is the last
@@ -701,13 +803,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     // i.e. published early in the kernel.  Publication needs no fence, counter or barrier: every
                     // 32-bit word of a slot is its own flag (0 = not yet written; a partial sum of +0.0f is stored
                     // as -0.0f, which adds identically), the reducer polls exactly the words it needs with relaxed
-                    // gpu-scope loads, adds them to its own partial (kept in registers) in ascending CTA order --
-                    // deterministic -- and stores the zeros back, which leaves the workspace clean for the next
-                    // launch.  Only one L2 round trip of the reducer sits on the kernel's tail.
-                    const long long tile_u0 = (long long)tile * p.units_per_tile;
-                    const int c_first = sk_owner(tile_u0, U, P);
-                    const int c_last = sk_owner(tile_u0 + p.units_per_tile - 1, U, P);
-                    if ((int)blockIdx.x != c_first) {
+                    // gpu-scope loads, adds them (ascending CTA order -- deterministic) and stores the zeros back,
+                    // which leaves the workspace clean for the next launch.
+                    if (!reducer) {
                         uint32_t* slot = reinterpret_cast<uint32_t*>(p.slots) + ((size_t)tile + blockIdx.x) * (MPAD * kTileN);
 #pragma unroll 1
                         for (int m0 = 0; m0 < MPAD; m0 += 16) {
@@ -737,64 +835,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                                 if (lane == 0) mbar_arrive(acc_empty);
                             }
                             if (!(m0 < p.M || p.mode == UMB_EPI_SILU_MUL)) continue;
-                            const int mcols = p.M - m0;
-                            uint32_t* sl0 = reinterpret_cast<uint32_t*>(p.slots) +
-                                            ((size_t)tile + c_first + 1) * (MPAD * kTileN) + m0 * kTileN + fl;
-                            if (mcols <= 4) {
-                                // few token rows (draft levels): 8 slots in flight per round trip
-                                for (int c0 = 0; c0 < n_other; c0 += 8) {
-                                    uint32_t t[8][4];
-                                    bool pending;
-                                    do {
-                                        pending = false;
+                            if (have_pre) {
 #pragma unroll
-                                        for (int cc = 0; cc < 8; ++cc)
-#pragma unroll
-                                            for (int j = 0; j < 4; ++j) {
-                                                const bool need = c0 + cc < n_other && j < mcols;
-                                                t[cc][j] = need ? ld_relaxed_gpu_u32(sl0 + (size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN) : 0x80000000u;
-                                            }
-#pragma unroll
-                                        for (int cc = 0; cc < 8; ++cc)
-#pragma unroll
-                                            for (int j = 0; j < 4; ++j) pending |= t[cc][j] == 0u;
-                                    } while (pending);
-#pragma unroll
-                                    for (int cc = 0; cc < 8; ++cc)
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
-                                            v[j] += __uint_as_float(t[cc][j]);
-                                            if (c0 + cc < n_other && j < mcols) sl0[(size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN] = 0u;
-                                        }
-                                }
-                            } else if (mcols > 0) {
-                                for (int c0 = 0; c0 < n_other; c0 += 2) {
-                                    uint32_t t[2][16];
-                                    bool pending;
-                                    do {
-                                        pending = false;
-#pragma unroll
-                                        for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-                                            for (int j = 0; j < 16; ++j) {
-                                                const bool need = c0 + cc < n_other && j < mcols;
-                                                t[cc][j] = need ? ld_relaxed_gpu_u32(sl0 + (size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN) : 0x80000000u;
-                                            }
-#pragma unroll
-                                        for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-                                            for (int j = 0; j < 16; ++j) pending |= t[cc][j] == 0u;
-                                    } while (pending);
-#pragma unroll
-                                    for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-                                        for (int j = 0; j < 16; ++j) {
-                                            v[j] += __uint_as_float(t[cc][j]);
-                                            if (c0 + cc < n_other && j < mcols) sl0[(size_t)(c0 + cc) * (MPAD * kTileN) + j * kTileN] = 0u;
-                                        }
-                                }
+                                for (int j = 0; j < 16; ++j) v[j] += pre[j];
+                            } else {
+                                reduce_others(v, m0, tile, c_first, n_other);
                             }
-                            epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
+                            epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch, have_res ? res_pre : nullptr);
                         }
                     }
                 }
@@ -949,7 +996,8 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? UMB_OK : UMB_ERR_ARG;
+    if (r != CUDA_SUCCESS) return arg_fail(__FILE__, __LINE__, "cuTensorMapEncodeTiled");
+    return UMB_OK;
 }
 
 // debug timeline (UMB_GEMM_TRACE=1): one device buffer, 16 stamps per CTA of the LAST gemm launch
