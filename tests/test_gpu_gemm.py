@@ -145,3 +145,30 @@ def test_gemm_f16_and_logits(M, K, N):
     assert torch.equal(ids, logits.cpu().argmax(-1))
     assert torch.equal(ops.argmax(logits).cpu(), ids)
     assert int(keys.abs().sum()) == 0                               # key buffer handed back clean
+
+
+def test_awq_kernels_vs_upstream_golden():
+    """umb_awq_dequantize_f16 is bit-identical to the upstream dequantize_weights kernel, and the tcgen05 GEMM
+    is at least as close to the exact product as the upstream gemm_forward kernel (tests/golden/awq_upstream.npz,
+    produced by oracle/make_golden_gpu.py from vLLM's build of the autoawq-kernels sources)."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "awq_upstream.npz")
+    if not os.path.exists(path):
+        pytest.skip("awq_upstream.npz not generated yet")
+    from umbrella_b200 import ops
+    z = np.load(path)
+    ci = 0
+    while "c%d_meta" % ci in z:
+        pre = "c%d_" % ci
+        m, k, n, g = map(int, z[pre + "meta"])
+        qw, qz, sc, x = (torch.from_numpy(z[pre + s]).to(DEV) for s in ("qweight", "qzeros", "scales", "x"))
+        deq = ops.awq_dequantize(qw, qz, sc)
+        assert torch.equal(deq.view(torch.int16).cpu(), torch.from_numpy(z[pre + "dequant"]).view(torch.int16)), ci
+        packed = ops.awq_repack(qw, qz, sc)
+        y = ops.awq_gemm(x, packed, k, n).float().cpu().numpy().astype(np.float64)
+        exact = oawq.gemm_exact(z[pre + "x"], z[pre + "qweight"], z[pre + "qzeros"], z[pre + "scales"], g)
+        scale = np.abs(exact).max()
+        err_up = np.abs(z[pre + "y"].astype(np.float64) - exact).max() / scale
+        err = np.abs(y - exact).max() / scale
+        assert err <= max(err_up, 1e-3), (ci, err, err_up)          # tolerance: no worse than the reference kernel
+        ci += 1
+    assert ci >= 4

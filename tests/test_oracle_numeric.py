@@ -3,6 +3,7 @@ fixtures of oracle/make_golden.py (reference Python on CPU / transformers / vLLM
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import attention as A
@@ -153,3 +154,31 @@ def test_tree_verify_is_lossless_on_oracle_model(golden_dir):
         steps += 1
     k = min(len(produced), len(want))
     assert k >= 8 and produced[:k] == want[:k]
+
+
+def test_awq_oracle_matches_upstream_kernel(golden_dir):
+    """Pins the AWQ arithmetic: tests/golden/awq_upstream.npz holds outputs of the UPSTREAM kernels
+    (vLLM 0.22's build of the autoawq-kernels sources the reference calls; oracle/make_golden_gpu.py, run on a
+    B200).  dequantize_weights: bit-exact.  gemm_forward (split_k_iters = 8, fp16 partial sums): the oracle's
+    emulation of its rounding and the exact-accumulation form both sit within fp16 noise of it."""
+    path = os.path.join(golden_dir, "awq_upstream.npz")
+    if not os.path.exists(path):
+        pytest.skip("awq_upstream.npz not generated yet (needs a GPU box)")
+    z = np.load(path)
+    ci = 0
+    while "c%d_meta" % ci in z:
+        pre = "c%d_" % ci
+        m, k, n, g = map(int, z[pre + "meta"])
+        qw, qz, sc, x = z[pre + "qweight"], z[pre + "qzeros"], z[pre + "scales"], z[pre + "x"]
+        deq = Q.dequantize(qw, qz, sc, g, np.float16)
+        assert deq.dtype == np.float16 and (deq.view(np.uint16) == z[pre + "dequant"].view(np.uint16)).all(), ci
+        y_up = z[pre + "y"].astype(np.float64)
+        exact = Q.gemm_exact(x, qw, qz, sc, g)
+        scale = np.abs(exact).max()
+        err_up = np.abs(y_up - exact).max() / scale                   # how far the upstream kernel is from the truth
+        err_ours = np.abs(Q.gemm_fp16_weights(x, qw, qz, sc, g).astype(np.float64) - exact).max() / scale
+        assert err_up < 4e-3 and err_ours <= max(err_up, 1e-3), (ci, err_up, err_ours)
+        emu = Q.gemm_reference_emulated(x, qw, qz, sc, g).astype(np.float64)
+        assert np.abs(emu - y_up).max() / scale < 4e-3, ci
+        ci += 1
+    assert ci >= 4
