@@ -281,7 +281,8 @@ int umb_llama_forward_range(const umb_llama_t* model, const int64_t* input_ids, 
  * from n_dev[0] (the committed prefix length n, maintained by umb_tree_accept through `state`):
  * the rows are tokens_base[n + row_offset + r] / position_base[n + row_offset + r], they are
  * appended at cache rows n + row_offset + r, and row r sees [0, n) plus the set bits of
- * tree_bits[r, :] (offset n).  kv_len_bound >= n + row_offset + rows sizes the attention grid.
+ * tree_bits[r, :] (offset n).  row_offset = -1 starts one row before the tree (the last committed token): the
+ * prefix is then n - 1 and the bits are relative to it.  kv_len_bound >= n + row_offset + rows sizes the attention grid.
  * rows <= 128.  One captured CUDA graph of this call is valid until n exceeds the bound. */
 int umb_llama_forward_dyn(const umb_llama_t* model, const int64_t* tokens_base, const int64_t* position_base,
                           int rows, const int32_t* n_dev, int row_offset, int kv_len_bound,

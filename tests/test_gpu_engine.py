@@ -24,11 +24,11 @@ DRAFT = ollama.LlamaShape(hidden_size=256, intermediate_size=512, num_hidden_lay
                           rope_theta=10000.0)
 
 
-def _engine(tree="sequoia_tree-3x4.json", S=384, draft_same=False, graph=True):
+def _engine(tree="sequoia_tree-3x4.json", S=384, draft_same=False, graph=True, lazy=True):
     from umbrella_b200.models.llama import SyntheticLlama
     from umbrella_b200.speculation.static_speculation_engine import StaticSpeculationEngine
     eng = StaticSpeculationEngine("draft", "target", device=DEV, growmap_path=tree, max_length=S, safe_buffer=48,
-                                  graph_iteration=graph, graph_bucket=128)
+                                  graph_iteration=graph, graph_bucket=128, lazy_leaf_kv=lazy)
     target = SyntheticLlama(TARGET, max_length=S, awq=True, seed=21, device=DEV)
     draft = SyntheticLlama(TARGET, max_length=S, awq=True, seed=21, device=DEV) if draft_same else \
         SyntheticLlama(DRAFT, max_length=S, awq=False, seed=22, device=DEV)
@@ -133,3 +133,43 @@ def test_graph_iteration_equals_eager_under_script():
     assert outs[0]["generated_tokens"] == outs[1]["generated_tokens"]
     assert outs[0]["large_model_steps"] == outs[1]["large_model_steps"]
     assert outs[0]["avg_accept_tokens"] > 2.5
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_lazy_leaf_kv_equals_reference_schedule(graph):
+    """lazy_leaf_kv (no draft forward for the leaf level; an accepted leaf's K/V is recomputed by the next
+    iteration's first draft step) against the reference schedule (one draft forward per level): same scripted
+    acceptance -> identical tokens and step counts, and the draft cache holds the same rows (fp16 noise: the
+    recomputed row sees its keys at compacted positions) except the last committed one, which is still pending."""
+    from umbrella_b200.speculation.scripted import ScriptedAcceptance
+    g = torch.Generator().manual_seed(12)
+    prompt = torch.randint(3, TARGET.vocab_size, (1, 45), generator=g).to(DEV)
+    caches, toks, steps = [], [], []
+    for lazy in (False, True):
+        eng = _engine(draft_same=True, graph=graph, lazy=lazy)
+        eng.acceptance_script = ScriptedAcceptance(eng.Successors, seed=3, max_iters=64, device=DEV)
+        assert eng._prefill(prompt)
+        for _ in range(14):
+            eng.build_tree()
+            eng.verify()
+        n = eng.num_nodes
+        toks.append(eng.tokens[0, :n + 1].cpu())
+        steps.append(n)
+        caches.append((eng.draft_model.kv_cache.k_cache[:, :n - 1].float().cpu(),
+                       eng.draft_model.kv_cache.v_cache[:, :n - 1].float().cpu()))
+        assert eng.draft_model.kv_cache.kv_offset == n
+    assert steps[0] == steps[1] and torch.equal(toks[0], toks[1])
+    for a, b in zip(caches[0], caches[1]):
+        assert torch.allclose(a, b, atol=4e-3, rtol=2e-2)
+
+
+def test_lazy_leaf_kv_keeps_draft_quality():
+    """Greedy decoding with the draft identical to the target: whole chains are accepted with either draft
+    schedule, i.e. the lazily recomputed rows are as good as the eagerly computed ones."""
+    g = torch.Generator().manual_seed(6)
+    prompt = torch.randint(3, TARGET.vocab_size, (50,), generator=g).tolist()
+    outs = [_engine(draft_same=True, graph=True, lazy=lazy).generate(input_ids=prompt, max_new_tokens=96)
+            for lazy in (False, True)]
+    assert outs[0]["generated_tokens"][:96] == outs[1]["generated_tokens"][:96]
+    assert abs(outs[0]["large_model_steps"] - outs[1]["large_model_steps"]) <= 2
+    assert outs[1]["avg_accept_tokens"] > 3.0

@@ -148,13 +148,15 @@ extern "C" int umb_llama_forward_dyn(const umb_llama_t* m, const int64_t* tokens
                                      const uint32_t* tree_bits, int tree_words, float* logits,
                                      unsigned long long* argmax_keys, umb_stream_t stream) {
     UMB_CHECK_ARG(m && tokens_base && position_base && n_dev && tree_bits && rows >= 1 && rows <= 128);
-    UMB_CHECK_ARG(row_offset >= 0 && tree_words >= 1 && kv_len_bound >= row_offset + rows && kv_len_bound <= m->max_length);
+    // row_offset = -1: the rows start at the last committed token (n - 1), which then counts as prefix n - 1 --
+    // the draft's first step re-derives that token's K/V together with the root (lazily computed leaf rows)
+    UMB_CHECK_ARG(row_offset >= -1 && tree_words >= 1 && kv_len_bound >= row_offset + rows && kv_len_bound <= m->max_length);
     UMB_CHECK_ARG(m->layers && m->embed && m->final_norm && m->cos && m->sin && m->k_cache && m->v_cache);
     UMB_CHECK_ARG(m->hidden && m->normed && m->qkv && m->q_rot && m->attn_out && m->act && m->gemm_ws);
     UMB_CHECK_ARG(!argmax_keys || logits);
     umb_attn_mask_t mk{};
     mk.mask_mode = UMB_MASK_TREE;
-    mk.prefix_len = 0;                 // offsets relative to n_dev[0]
+    mk.prefix_len = row_offset < 0 ? row_offset : 0;   // offsets relative to n_dev[0]
     mk.dyn = n_dev;
     mk.tree_bits = tree_bits;
     mk.tree_words = tree_words;

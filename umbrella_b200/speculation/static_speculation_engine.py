@@ -49,6 +49,12 @@ class StaticSpeculationEngine(BaseEngine):
         # launch and the host reads back 3 ints.  Greedy decoding only; other settings run eagerly.
         self.graph_iteration = kwargs.pop("graph_iteration", True)
         self.graph_bucket = kwargs.pop("graph_bucket", 512)
+        # Draft-side schedule.  The reference runs one draft forward per tree level, the last one only to put
+        # the leaves' K/V into the draft cache (static...:257-281).  With lazy_leaf_kv the leaf level is not run:
+        # a leaf's K/V is needed only if that leaf is accepted, and then it is the LAST committed token -- the
+        # next iteration's first draft step recomputes it, feeding [last committed token, root] as two causal
+        # rows.  One draft forward fewer per iteration; the accepted tokens are unchanged (they are the target's).
+        self.lazy_leaf_kv = kwargs.pop("lazy_leaf_kv", True)
         self.draft_model = None
         self.target_model = None
         self.stats = {"verify_calls": 0}
@@ -117,8 +123,9 @@ class StaticSpeculationEngine(BaseEngine):
         self._graphs = {}
         self._tree_pending = False
         V = self.vocab_size
-        self._draft_logits = [torch.empty((b - a, self.draft_model.config.vocab_size), dtype=torch.float32, device=dev)
-                              for (a, b) in self.level_ranges[:-1]]
+        self._draft_logits = [torch.empty((b - a + (1 if a == 0 else 0), self.draft_model.config.vocab_size),
+                                          dtype=torch.float32, device=dev) for (a, b) in self.level_ranges[:-1]]
+        self._root_bits = torch.tensor([[1], [3]], dtype=torch.int32, device=dev)      # [prev, root]: causal pair
         self._target_logits = torch.empty((N, V), dtype=torch.float32, device=dev)
 
     def _set_eos(self, eos_tokens):
@@ -181,6 +188,9 @@ class StaticSpeculationEngine(BaseEngine):
         return True
 
     # ------------------------------------------------------------------ the loop
+    def _lazy(self) -> bool:
+        return bool(self.lazy_leaf_kv) and self.tree_depth >= 2 and self.num_nodes >= 1
+
     def _graph_ok(self) -> bool:
         return bool(self.graph_iteration) and self.temperature < 0.05 and not (self.repetition_penalty > 1.01)
 
@@ -188,11 +198,16 @@ class StaticSpeculationEngine(BaseEngine):
         """Enqueue one whole iteration with every position read from the device state word."""
         N = self.tree_size
         tok, pos, st = self.tokens[0], self.position_ids[0], self._state
-        for step in range(self.tree_depth):
+        lazy = self._lazy()
+        for step in range(self.tree_depth - 1 if lazy else self.tree_depth):
             a, b = self.level_ranges[step]
             last = step == self.tree_depth - 1
-            lg = None if last else self._draft_logits[step]
-            self.draft_model.forward_dyn(tok, pos, b - a, st, a, bound, self.tree_bits[a:b], logits=lg)
+            lg = None if last else self._draft_logits[step][:b - a]
+            if lazy and step == 0:
+                self.draft_model.forward_dyn(tok, pos, 2, st, -1, bound, self._root_bits, logits=self._draft_logits[0])
+                lg = self._draft_logits[0][1:2]
+            else:
+                self.draft_model.forward_dyn(tok, pos, b - a, st, a, bound, self.tree_bits[a:b], logits=lg)
             if not last:
                 width = max(self.branch_lists[step])
                 new_tokens = lg.topk(k=width).indices.flatten().index_select(0, self.sample_gather_indices[step])
@@ -249,18 +264,27 @@ class StaticSpeculationEngine(BaseEngine):
             self._tree_pending = True          # the draft levels run inside verify()'s iteration graph
             return
         n = self.num_nodes
-        for step in range(self.tree_depth):
+        lazy = self._lazy()
+        for step in range(self.tree_depth - 1 if lazy else self.tree_depth):
             a, b = self.level_ranges[step]
-            ids = self.tokens[0, n + a:n + b]
-            pos = self.position_ids[0, n + a:n + b]
             last = step == self.tree_depth - 1
-            logits = self.draft_model.verify_forward(ids, pos, n, self.tree_bits[a:b], want_logits=not last)
+            if lazy and step == 0:
+                self.draft_model.kv_cache.kv_offset = n - 1
+                logits = self.draft_model.verify_forward(self.tokens[0, n - 1:n + 1], self.position_ids[0, n - 1:n + 1],
+                                                         n - 1, self._root_bits)[1:]
+            else:
+                ids = self.tokens[0, n + a:n + b]
+                pos = self.position_ids[0, n + a:n + b]
+                logits = self.draft_model.verify_forward(ids, pos, n, self.tree_bits[a:b], want_logits=not last)
             self.num_draft_tokens_this_iter += b - a
             if not last:
                 width = max(self.branch_lists[step])
                 new_tokens = logits.topk(k=width).indices.flatten().index_select(0, self.sample_gather_indices[step])
                 total = new_tokens.numel()
                 self.tokens[0, n + b:n + b + total] = new_tokens
+        if lazy:       # leaf rows stay unwritten; the gather treats the cache as holding all N tree rows
+            self.draft_model.kv_cache.kv_offset = n + self.tree_size
+            self.num_draft_tokens_this_iter = n + self.tree_size
 
     def _sample_target(self, logits: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
         """static...:298-310.  Greedy: decode the arg-max keys produced by the lm_head epilogue."""
