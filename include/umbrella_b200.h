@@ -79,8 +79,27 @@ enum {
     UMB_EPI_RESIDUAL = 1, /* y[m, n] = fp16(acc) +_fp16 residual[m, n]   (llama.py:293,301)      */
     UMB_EPI_SILU_MUL = 2, /* packed rows interleave 64 gate | 64 up per tile;
                              y[m, 64 t + r] = fp16(silu(fp16(gate))) *_fp16 fp16(up)  (llama.py:296-299) */
-    UMB_EPI_LOGITS = 3    /* y is fp32 [M, N]: float(fp16(acc)); optional running arg-max keys   */
+    UMB_EPI_LOGITS = 3,   /* y is fp32 [M, N]: float(fp16(acc)); optional running arg-max keys   */
+    UMB_EPI_ROPE_QKV = 4  /* fused q|k|v projection: fp16(acc) (+ bias), RoPE on the q and k heads (the three rounded
+                             fp16 ops of apply_rotary_pos_emb, model_utils.py:17-52), q -> q_out [M, Hq, D], k / v
+                             appended to the cache rows (update_kv_cache, cache.py:53-65); y is not written.
+                             N_total == (Hq + 2 Hkv) * D, D in {64, 128}                                  */
 };
+/* Operands of UMB_EPI_ROPE_QKV (same meaning as umb_rope_append_f16's). */
+typedef struct {
+    void* q_out;
+    void* k_cache;
+    void* v_cache;
+    const void* cos;
+    const void* sin;
+    const int64_t* position_ids;   /* n_dev == NULL: positions of the M rows; else the base array               */
+    const int32_t* n_dev;          /* optional device int32 n: rows are tokens n + row_offset + m, appended at
+                                      cache rows n + kv_offset + m (graph replay)                               */
+    int row_offset;
+    int kv_offset;                 /* n_dev == NULL: absolute append position                                   */
+    int num_q_heads, num_kv_heads, head_dim;
+    int64_t kv_tok_stride, kv_head_stride;
+} umb_rope_epilogue_t;
 typedef struct {
     int mode;
     const void* bias;            /* fp16 [N] or NULL                                              */
@@ -88,6 +107,7 @@ typedef struct {
     int64_t ld_residual;
     unsigned long long* argmax;  /* mode 3: [M] keys, (orderable(fp16 logit) << 32) | ~index; caller
                                     zero-fills; NULL = no arg-max                                  */
+    const umb_rope_epilogue_t* rope;   /* mode 4 only (read at launch time)                          */
 } umb_epilogue_t;
 
 size_t umb_gemm_workspace_bytes(int M, int K, int N_total);

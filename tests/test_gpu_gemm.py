@@ -172,3 +172,62 @@ def test_awq_kernels_vs_upstream_golden():
         assert err <= max(err_up, 1e-3), (ci, err, err_up)          # tolerance: no worse than the reference kernel
         ci += 1
     assert ci >= 4
+
+
+@pytest.mark.parametrize("awq,M,Hq,Hkv,D,K", [(True, 13, 8, 2, 128, 1024), (True, 3, 4, 1, 64, 512), (False, 31, 4, 2, 64, 256),
+                                             (True, 97, 4, 4, 128, 512), (False, 1, 8, 8, 128, 512)])
+def test_fused_rope_qkv_epilogue_is_bit_identical(awq, M, Hq, Hkv, D, K):
+    """UMB_EPI_ROPE_QKV (q|k|v GEMM + RoPE + KV append in one kernel) writes exactly the bits of the two-kernel
+    path (GEMM store, then umb_rope_append_f16): same fp16 rounding points, same three rounded rotary ops."""
+    from umbrella_b200 import ops
+    rng = np.random.default_rng(M + D)
+    N, S, off = (Hq + 2 * Hkv) * D, 256, 77
+    x = torch.from_numpy((rng.standard_normal((M, K)) * 0.7).astype(np.float16)).to(DEV)
+    if awq:
+        qw, qz, sc = oawq.random_awq(K, N, 128, rng, scale=0.02)
+        packed = ops.awq_repack(*(torch.from_numpy(t).to(DEV) for t in (qw, qz, sc)))
+        gemm = lambda **kw: ops.awq_gemm(x, packed, K, N, **kw)
+    else:
+        w = torch.from_numpy((rng.standard_normal((N, K)) * 0.05).astype(np.float16)).to(DEV)
+        gemm = lambda **kw: ops.gemm_f16(x, w, **kw)
+    pos = torch.from_numpy(rng.integers(0, S, M)).to(DEV)
+    ang = torch.rand(S, D, device=DEV) * 6.28
+    cos, sin = ang.cos().to(torch.float16), ang.sin().to(torch.float16)
+    outs = []
+    for fused in (False, True):
+        q_out = torch.zeros(M, Hq, D, dtype=torch.float16, device=DEV)
+        kc = torch.zeros(S, Hkv, D, dtype=torch.float16, device=DEV)
+        vc = torch.zeros_like(kc)
+        if fused:
+            rp = ops.make_rope_epilogue(q_out, kc, vc, cos, sin, pos, Hq, Hkv, D, off)
+            gemm(mode=ops.UMB_EPI_ROPE_QKV, rope=rp, out=torch.zeros(M, N, dtype=torch.float16, device=DEV))
+        else:
+            qkv = gemm()
+            ops.rope_append(qkv, q_out, kc, vc, cos, sin, pos, Hq, Hkv, D, off)
+        outs.append((q_out, kc, vc))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert outs[1][1][off:off + M].abs().sum() > 0 and outs[1][1][:off].abs().sum() == 0
+
+
+@pytest.mark.parametrize("M", [65, 97, 128])
+def test_rows_above_64_are_stable_and_correct(M):
+    """Regression for the rare launch failure of the 128-column GEMM instantiation (scripts/repro_m128.py): calls
+    with 65..128 rows run as two launches of <= 64 rows; 200 back-to-back launches at a 70B q|k|v shape must all
+    succeed, leave the workspace clean and agree with the first result bit for bit (deterministic reduction)."""
+    from umbrella_b200 import ops
+    K, N = 8192, 10240
+    rng = np.random.default_rng(M)
+    qw, qz, sc = oawq.random_awq(K, N, 128, rng)
+    packed = ops.awq_repack(*(torch.from_numpy(t).to(DEV) for t in (qw, qz, sc)))
+    x = torch.from_numpy((rng.standard_normal((M, K)) * 0.5).astype(np.float16)).to(DEV)
+    ws = ops.gemm_workspace(M, K, N, DEV)
+    first = ops.awq_gemm(x, packed, K, N, workspace=ws).clone()
+    for _ in range(200):
+        y = ops.awq_gemm(x, packed, K, N, workspace=ws)
+    torch.cuda.synchronize()
+    assert torch.equal(y, first)
+    assert int(ws.view(torch.int32).abs().max()) == 0
+    w16 = ops.awq_unpack(packed, K, N).float()                       # [N, K] fp16 weights as the kernel sees them
+    ref = x.float() @ w16.t()
+    assert float((y.float() - ref).abs().max() / ref.abs().max()) < 2e-3

@@ -15,13 +15,20 @@ LIB_PATH = os.environ.get("UMB_LIB_PATH") or os.path.join(HERE, "libumbrella_b20
 
 c_void_p, c_int, c_int64, c_size_t, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
 
-UMB_EPI_STORE, UMB_EPI_RESIDUAL, UMB_EPI_SILU_MUL, UMB_EPI_LOGITS = 0, 1, 2, 3
+UMB_EPI_STORE, UMB_EPI_RESIDUAL, UMB_EPI_SILU_MUL, UMB_EPI_LOGITS, UMB_EPI_ROPE_QKV = 0, 1, 2, 3, 4
 UMB_MASK_TREE, UMB_MASK_DENSE, UMB_MASK_CAUSAL = 0, 1, 2
 
 
 class Epilogue(C.Structure):
     _fields_ = [("mode", c_int), ("bias", c_void_p), ("residual", c_void_p), ("ld_residual", c_int64),
-                ("argmax", c_void_p)]
+                ("argmax", c_void_p), ("rope", c_void_p)]
+
+
+class RopeEpilogue(C.Structure):
+    _fields_ = [("q_out", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p), ("cos", c_void_p), ("sin", c_void_p),
+                ("position_ids", c_void_p), ("n_dev", c_void_p), ("row_offset", c_int), ("kv_offset", c_int),
+                ("num_q_heads", c_int), ("num_kv_heads", c_int), ("head_dim", c_int), ("kv_tok_stride", c_int64),
+                ("kv_head_stride", c_int64)]
 
 
 class AttnMask(C.Structure):

@@ -17,6 +17,22 @@ bool pdl_enabled() {
     }
     return cached != 0;
 }
+bool sync_debug() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("UMB_SYNC_DEBUG");
+        cached = (e && e[0] == '1') ? 1 : 0;
+    }
+    return cached != 0;
+}
+cudaError_t sync_debug_check(const char* name, dim3 grid, dim3 block, cudaStream_t st, cudaError_t launch_rc) {
+    cudaError_t rc = launch_rc;
+    if (rc == cudaSuccess) rc = cudaStreamSynchronize(st);
+    if (rc != cudaSuccess)
+        fprintf(stderr, "umbrella_b200: kernel %s grid (%u,%u,%u) block %u failed: %s\n", name, grid.x, grid.y, grid.z,
+                block.x, cudaGetErrorString(rc));
+    return rc;
+}
 int arg_fail(const char* file, int line, const char* what) {
     static int dbg = -1;
     if (dbg < 0) {

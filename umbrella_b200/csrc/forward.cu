@@ -2,6 +2,8 @@
 // kernels).  Mirrors LlamaAwq.inference / layer_compute (reference umbrella/models/llama.py:262-322)
 // and Llama.inference (llama.py:75-134) op for op; every fp16 rounding point of the reference is a
 // kernel boundary or an explicit rounding inside a fused epilogue here.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -15,6 +17,18 @@ static int linear(const umb_llama_t* m, const void* x, int64_t ldx, const void* 
 }
 
 #define UMB_TRY(expr) do { int rc__ = (expr); if (rc__ != UMB_OK) return rc__; } while (0)
+
+constexpr int kChunkRows = 64;
+
+// UMB_FUSE_ROPE=0 keeps the separate rope_append kernel (A/B switch; read once)
+static bool fuse_rope() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("UMB_FUSE_ROPE");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached != 0;
+}
 
 // n_dev == NULL: ids / pos point at the rows, kv_offset is the append position (host value).
 // n_dev != NULL: ids / pos are base pointers, kv_offset is the row offset added to n_dev[0] on the device.
@@ -38,6 +52,28 @@ static int forward_chunk(const umb_llama_t* m, const int64_t* ids, const int64_t
         __half* kc = (__half*)m->k_cache + l * layer_elems;
         __half* vc = (__half*)m->v_cache + l * layer_elems;
         UMB_TRY(umb_rmsnorm_f16(m->hidden, L.input_norm, m->normed, rows, H, m->rms_eps, st));
+        if (fuse_rope() && (D == 64 || D == 128)) {
+            // q|k|v projection + RoPE + KV append in one kernel (UMB_EPI_ROPE_QKV)
+            umb_rope_epilogue_t rp{};
+            rp.q_out = m->q_rot;
+            rp.k_cache = kc;
+            rp.v_cache = vc;
+            rp.cos = m->cos;
+            rp.sin = m->sin;
+            rp.position_ids = pos;
+            rp.n_dev = n_dev;
+            rp.row_offset = kv_offset;
+            rp.kv_offset = kv_offset;
+            rp.num_q_heads = Hq;
+            rp.num_kv_heads = Hkv;
+            rp.head_dim = D;
+            rp.kv_tok_stride = tok_stride;
+            rp.kv_head_stride = D;
+            umb_epilogue_t qe{};
+            qe.mode = UMB_EPI_ROPE_QKV;
+            qe.rope = &rp;
+            UMB_TRY(linear(m, m->normed, H, L.wqkv, m->qkv, qkv_n, rows, H, qkv_n, &qe, st));
+        } else {
         UMB_TRY(linear(m, m->normed, H, L.wqkv, m->qkv, qkv_n, rows, H, qkv_n, nullptr, st));
         if (n_dev)
             UMB_TRY(rope_append_dyn(m->qkv, qkv_n, m->q_rot, kc, vc, m->cos, m->sin, pos, n_dev, kv_offset, rows, Hq, Hkv,
@@ -45,6 +81,7 @@ static int forward_chunk(const umb_llama_t* m, const int64_t* ids, const int64_t
         else
             UMB_TRY(umb_rope_append_f16(m->qkv, qkv_n, m->q_rot, kc, vc, m->cos, m->sin, pos, rows, Hq, Hkv, D,
                                         tok_stride, D, kv_offset, nullptr, st));
+        }
         UMB_TRY(umb_tree_attn_f16(m->q_rot, kc, vc, m->attn_out, rows, kv_offset + rows, Hq, Hkv, D, tok_stride, D,
                                   mask, 0.f, 0.f, m->attn_ws, m->attn_ws_bytes, st));
         umb_epilogue_t res{};
@@ -97,9 +134,10 @@ extern "C" int umb_llama_forward(const umb_llama_t* m, const int64_t* input_ids,
     UMB_CHECK_ARG(kv_offset + rows <= m->max_length);
     UMB_CHECK_ARG(!argmax_keys || logits);
     if (logits) UMB_CHECK_ARG(m->lm_head != nullptr);
-    // rows > 128 (prefill, dynamic trees of 257..505 nodes): equal chunks of <= 128 rows, each a full pass
-    // over the weights; later chunks see the KV rows the earlier ones appended
-    const int n_chunks = (rows + 127) / 128;
+    // rows > 64 (prefill, dynamic trees of 257..505 nodes): equal chunks of <= 64 rows, each a full pass
+    // over the weights; later chunks see the KV rows the earlier ones appended.  (64, not 128: the GEMM's
+    // 128-column instantiation is held back, see gemm_common.)
+    const int n_chunks = (rows + umb::kChunkRows - 1) / umb::kChunkRows;
     const int chunk = (rows + n_chunks - 1) / n_chunks;
     for (int r0 = 0; r0 < rows; r0 += chunk) {
         const int n = rows - r0 < chunk ? rows - r0 : chunk;

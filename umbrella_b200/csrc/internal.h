@@ -13,9 +13,12 @@ namespace umb {
 // is still draining.  Each such kernel executes griddepcontrol.wait before touching global memory a
 // predecessor wrote, and before completing (transitivity of the chain).  UMB_PDL=0 disables it.
 bool pdl_enabled();
+// UMB_SYNC_DEBUG=1: synchronise after every launch and name the kernel that faulted (debugging aid)
+bool sync_debug();
+cudaError_t sync_debug_check(const char* name, dim3 grid, dim3 block, cudaStream_t st, cudaError_t launch_rc);
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              Args&&... args) {
+inline cudaError_t launch_pdl(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -26,9 +29,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    return sync_debug() ? sync_debug_check(name, grid, block, st, rc) : rc;
 }
-#define UMB_LAUNCH_PDL(...) do { cudaError_t e__ = umb::launch_pdl(__VA_ARGS__); if (e__ != cudaSuccess) return (int)e__; } while (0)
+#define UMB_LAUNCH_PDL(kernel, ...) do { cudaError_t e__ = umb::launch_pdl(#kernel, kernel, __VA_ARGS__); if (e__ != cudaSuccess) return (int)e__; } while (0)
 // every host entry point reports the kernels it enqueued (umb_launch_count)
 void count_launches(unsigned n);
 // number of SMs of the current device (cached)

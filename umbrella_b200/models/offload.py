@@ -32,6 +32,7 @@ from .. import _lib, ops
 from .llama import MAX_ROWS, Llama, LlamaAwq
 
 _ALIGN = 256
+CHUNK_ROWS = 64      # rows per chunk of a paged forward (matches kChunkRows of csrc/forward.cu)
 _PARTS = ("wqkv", "wo", "wgu", "wdown", "input_norm", "post_norm")
 
 
@@ -155,7 +156,7 @@ class _Paged:
             raise RuntimeError(f"KV cache overflow: {kv_offset} + {rows} > {self.max_length}")
         lib, cur = _lib.load(), torch.cuda.current_stream()
         st = C.c_void_p(cur.cuda_stream)
-        n_chunks = (rows + MAX_ROWS - 1) // MAX_ROWS
+        n_chunks = (rows + CHUNK_ROWS - 1) // CHUNK_ROWS
         chunk = (rows + n_chunks - 1) // n_chunks
         spans = [(r0, min(chunk, rows - r0)) for r0 in range(0, rows, chunk)]
         models = self._chunk_models(len(spans))

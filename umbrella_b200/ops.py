@@ -10,8 +10,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (AttnMask, Epilogue, UMB_EPI_LOGITS, UMB_EPI_RESIDUAL, UMB_EPI_SILU_MUL, UMB_EPI_STORE,
-                   UMB_MASK_CAUSAL, UMB_MASK_DENSE, UMB_MASK_TREE, check)
+from ._lib import (AttnMask, Epilogue, RopeEpilogue, UMB_EPI_LOGITS, UMB_EPI_RESIDUAL, UMB_EPI_ROPE_QKV, UMB_EPI_SILU_MUL,
+                   UMB_EPI_STORE, UMB_MASK_CAUSAL, UMB_MASK_DENSE, UMB_MASK_TREE, check)
 
 GROUP = 128
 
@@ -80,13 +80,30 @@ def gemm_workspace(M: int, K: int, N_total: int, device) -> torch.Tensor:
     return torch.zeros(n, dtype=torch.uint8, device=device)
 
 
-def _epilogue(mode, bias=None, residual=None, argmax=None):
+def make_rope_epilogue(q_out, k_cache, v_cache, cos, sin, position_ids, Hq: int, Hkv: int, D: int, kv_offset: int,
+                       layout: str = "NHD", n_dev=None, row_offset: int = 0) -> RopeEpilogue:
+    """Operands of UMB_EPI_ROPE_QKV: k/v = one layer of the cache ([S, Hkv, D] "NHD" or [Hkv, S, D] "HND")."""
+    r = RopeEpilogue()
+    r.q_out, r.k_cache, r.v_cache = q_out.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr()
+    r.cos, r.sin, r.position_ids = cos.data_ptr(), sin.data_ptr(), position_ids.data_ptr()
+    r.n_dev = n_dev.data_ptr() if n_dev is not None else None
+    r.row_offset, r.kv_offset = row_offset, kv_offset
+    r.num_q_heads, r.num_kv_heads, r.head_dim = Hq, Hkv, D
+    r.kv_tok_stride, r.kv_head_stride = (k_cache.stride(0), k_cache.stride(1)) if layout == "NHD" else \
+        (k_cache.stride(1), k_cache.stride(0))
+    return r
+
+
+def _epilogue(mode, bias=None, residual=None, argmax=None, rope=None):
     e = Epilogue()
     e.mode = mode
     e.bias = bias.data_ptr() if bias is not None else None
     e.residual = residual.data_ptr() if residual is not None else None
     e.ld_residual = residual.stride(0) if residual is not None else 0
     e.argmax = argmax.data_ptr() if argmax is not None else None
+    if rope is not None:
+        e._rope_keepalive = rope                       # the struct is read at launch time
+        e.rope = C.addressof(rope)
     return e
 
 
@@ -99,7 +116,7 @@ def _gemm_out(x, N_out, mode, out):
 
 def awq_gemm(x: torch.Tensor, packed: torch.Tensor, K: int, N_total: int, *, mode: int = UMB_EPI_STORE, bias=None,
              residual=None, argmax=None, out: torch.Tensor | None = None, workspace: torch.Tensor | None = None,
-             group: int = GROUP) -> torch.Tensor:
+             group: int = GROUP, rope: RopeEpilogue | None = None) -> torch.Tensor:
     """y[M, N] = x[M, K] . W from the packed stream (M <= 128)."""
     _cuda(x, torch.float16, "x")
     assert x.dim() == 2 and x.shape[1] == K and x.stride(1) == 1
@@ -107,7 +124,7 @@ def awq_gemm(x: torch.Tensor, packed: torch.Tensor, K: int, N_total: int, *, mod
     out = _gemm_out(x, N_out, mode, out)
     if workspace is None:
         workspace = gemm_workspace(x.shape[0], K, N_total, x.device)
-    e = _epilogue(mode, bias, residual, argmax)
+    e = _epilogue(mode, bias, residual, argmax, rope)
     check(_lib.load().umb_awq_gemm_f16(_p(x), x.stride(0), _p(packed), _p(out), out.stride(0), x.shape[0], K, N_total,
                                        group, C.byref(e), _p(workspace), workspace.numel(), _stream()), "awq_gemm")
     return out
@@ -121,7 +138,7 @@ def awq_gemm_simt(x, packed, K, N_total):
 
 
 def gemm_f16(x: torch.Tensor, w: torch.Tensor, *, mode: int = UMB_EPI_STORE, bias=None, residual=None, argmax=None,
-             out=None, workspace=None) -> torch.Tensor:
+             out=None, workspace=None, rope: RopeEpilogue | None = None) -> torch.Tensor:
     """y = x . w^T for fp16 w [N, K] (torch Linear layout), M <= 128."""
     _cuda(x, torch.float16, "x"), _cuda(w, torch.float16, "w")
     N, K = w.shape
@@ -130,7 +147,7 @@ def gemm_f16(x: torch.Tensor, w: torch.Tensor, *, mode: int = UMB_EPI_STORE, bia
     out = _gemm_out(x, N_out, mode, out)
     if workspace is None:
         workspace = gemm_workspace(x.shape[0], K, N, x.device)
-    e = _epilogue(mode, bias, residual, argmax)
+    e = _epilogue(mode, bias, residual, argmax, rope)
     check(_lib.load().umb_gemm_f16(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), x.shape[0], K, N,
                                    C.byref(e), _p(workspace), workspace.numel(), _stream()), "gemm_f16")
     return out
