@@ -72,14 +72,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// Same wait for warps that are off the critical path (epilogue waiting for a whole tile, the producer
-// waiting for a stage to drain): a failed poll puts the warp to sleep instead of re-issuing at once, so
-// the spinning does not take issue slots from the dequant warps on the same scheduler.
-template <int kSleepNs>
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(kSleepNs);
-}
-
 // Ring-buffer cursor: stage index + phase parity.
 struct Ring {
     uint32_t stage = 0, phase = 0;

@@ -49,27 +49,10 @@ constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each,
 constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1);   // producer + 2 MMA issuers + dequant groups + epilogue group (AWQ)
 constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
-// Experiment switches (variant builds, scripts/sweep_variants.sh).  Measured on B200 at M = 13, 70B shapes
-// (profiles/r1_gemm_experiments.txt), sum of the four GEMMs of a layer:
-//   defaults below 129.7 us | UMB_EARLY_W=4 131.0 | + UMB_SLEEP_WAIT=3 131.2 | + UMB_DQ_PIPELINE=1 135.9
-// i.e. none of them pays: the steady state is bound by the fp16x2 / lop3 issue rate of the dequant warps
-// (0.5 warp-instructions per cycle per scheduler for HFMA2/HMUL2/HADD2/LOP3, scripts/ubench/pipe_rates.cu).
-#ifndef UMB_DQ_PIPELINE
-#define UMB_DQ_PIPELINE 0      // 1: fetch the next unit's packed words under the tcgen05.st of the current one
-#endif
-#ifndef UMB_SLEEP_WAIT
-#define UMB_SLEEP_WAIT 0       // bit 0: producer, bit 1: epilogue warps sleep between mbarrier polls
-#endif
-#ifndef UMB_EARLY_REDUCE
-#define UMB_EARLY_REDUCE 0     // 1: epilogue warps fetch residual rows / other CTAs' partials before their own
-                               // accumulators (measured: 130.2 us vs 126.4 us per layer without -- left off)
-#endif
-#ifndef UMB_EARLY_W_F16
-#define UMB_EARLY_W_F16 16     // same, fp16-weight GEMMs (2 measured 5.09 ms vs 4.98 ms for the five draft levels)
-#endif
-#ifndef UMB_EARLY_W
-#define UMB_EARLY_W 16         // weight records requested before griddepcontrol.wait (>= ring depth: all)
-#endif
+// Pipeline variants that were built, measured on B200 and rejected (sleeping mbarrier polls in the idle warps,
+// software-pipelined dequant, x slabs ahead of the weight ring, early residual fetch / early partial-sum
+// reduction, a fourth dequant group) are recorded in profiles/r1_gemm_experiments.txt; none beat this form,
+// whose steady state is bound by the fp16x2 issue rate of the dequant warps (scripts/ubench/pipe_rates.cu).
 
 // nibble position of the i-th of 8 consecutive values inside a 32-bit word: (0,4,1,5,2,6,3,7).
 // Used by the AutoAWQ checkpoint layout (along N) and by our repacked stream (along K): nibbles p
@@ -195,15 +178,6 @@ __device__ __forceinline__ void dequant_word(uint32_t w, uint32_t magic, __half2
                                              uint32_t* out) {
     const __half2 sixteenth = as_h2(0x2C002C00u);                 // 1/16
     const uint32_t w8 = w >> 8;
-#ifdef UMB_EXPERIMENT_ONE_FMA
-    // timing experiment only (numerically wrong): one half2 op per nibble pair instead of two
-    out[0] = as_u32(__hfma2(as_h2(lop3_and_or<0x000f000fu>(w, magic)), s2, neg_co));
-    out[1] = as_u32(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w, magic)), s2, neg_co));
-    out[2] = as_u32(__hfma2(as_h2(lop3_and_or<0x000f000fu>(w8, magic)), s2, neg_co));
-    out[3] = as_u32(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w8, magic)), s2, neg_co));
-    (void)ce; (void)sixteenth;
-    return;
-#endif
     // (t - ce) and fma(t, 1/16, -co) are exact; the multiply by the scale is the single rounding
     out[0] = as_u32(__hmul2(__hsub2(as_h2(lop3_and_or<0x000f000fu>(w, magic)), ce), s2));
     out[1] = as_u32(__hmul2(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w, magic)), sixteenth, neg_co), s2));
@@ -289,7 +263,7 @@ __device__ __forceinline__ unsigned int orderable_f32_g(float f) {
 // Epilogue of 16 token columns [m0, m0 + 16) for feature lane `fl` (0..127) of tile `tile`.
 template <int MPAD>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, int fl, int m0, const float (&v)[16],
-                                               __half* exch, const __half* res_pre = nullptr) {
+                                               __half* exch) {
     const int n = tile * kTileN + fl;
     if (p.mode == UMB_EPI_SILU_MUL) {
         // lanes 64..127 hold `up`, lanes 0..63 hold `gate` of output feature tile*64 + (fl & 63)
@@ -371,14 +345,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
     // store of the previous row would be serialised behind it (one L2 round trip per token row)
     __half res[16];
     if (p.mode == UMB_EPI_RESIDUAL) {
-        if (res_pre) {                                // loaded while the MMAs of this segment were still running
 #pragma unroll
-            for (int j = 0; j < 16; ++j) res[j] = res_pre[j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j < mcols) res[j] = p.residual[(int64_t)(m0 + j) * p.ld_residual + n];
-        }
+        for (int j = 0; j < 16; ++j)
+            if (j < mcols) res[j] = p.residual[(int64_t)(m0 + j) * p.ld_residual + n];
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -504,14 +473,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
         const unsigned char* src = p.packed + (kAwq ? u_begin * kRecordStride : 0);
         const int n_pre = n_units < kStages ? n_units : kStages;
-        // Only the first kEarlyW weight records are requested before griddepcontrol.wait: the copy engine
-        // serves its queue in order, so x slabs issued behind a full ring of weight copies would reach shared
-        // memory (and let the first MMA start) only after ~85 KB per SM had streamed in.
-        // (AWQ: the dequant warps, not the MMAs, set the pace, and prefetching the whole ring under the
-        // predecessor's tail measured slightly better -- UMB_EARLY_W = 16.  fp16 weights (draft model, lm_head):
-        // nothing happens between "landed" and "MMA", so the first x slab must not wait behind the ring.)
-        constexpr int kEarlyW = kAwq ? UMB_EARLY_W : UMB_EARLY_W_F16;
-        const int n_early = n_pre < kEarlyW ? n_pre : kEarlyW;
+        // The weight copies of the whole ring are requested before griddepcontrol.wait (they never depend on the
+        // stream predecessor), the x slabs after it.  (Requesting only a few records early, so that the first x
+        // slab does not queue behind ~85 KB of weights, starts the first MMA 2 us sooner but measured no faster:
+        // the dequant warps set the pace.)
+        const int n_early = n_pre;
         int tile = tile0, g = in_tile0;                          // (tile, g) of the next weight copy
         auto issue_w = [&](int stage) {
             mbar_arrive_expect_tx(full_w + stage, kWTxBytes);
@@ -562,11 +528,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         Ring r;
         r.phase = 1;                                             // every stage has been used once
         for (int i = n_pre; i < n_units; ++i) {
-#if UMB_SLEEP_WAIT & 1
-            mbar_wait_sleep<32>(done + r.stage, r.phase ^ 1);    // the unit that last used this stage has retired
-#else
-            mbar_wait(done + r.stage, r.phase ^ 1);
-#endif
+            mbar_wait(done + r.stage, r.phase ^ 1);              // the unit that last used this stage has retired
             if (elect_one()) {
                 issue_w(r.stage);
                 issue_x(r.stage, g);
@@ -660,9 +622,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 int w_first = grp;                                                 // first unit of this group that re-uses a TMEM stage
                 while (w_first < kAStages) w_first += kDqGroups;
                 int w_st = (w_first - kAStages) % kStages, w_ph = 0;               // ring position of unit `mine - kAStages`
-                // Software pipeline: the packed words / scale / zero of this group's NEXT unit are pulled into
-                // registers while the tcgen05.st of the current unit drains, so the shared-memory latency and
-                // the barrier poll of one unit hide behind the tensor-memory stores of the previous one.
+                // the packed words / scale / zero of a unit are pulled into registers as soon as its record has landed
                 uint4 w4[4];
                 uint32_t sbits = 0, zw = 0;
                 auto fetch = [&](int st_) {
@@ -710,19 +670,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         }
                         UMB_TMEM_ST_X16(taddr + c * 16, a);
                     }
-                    const bool more = mine + kDqGroups < n_units;
-                    // next record already in shared memory? then read it under the stores (warp-uniform answer)
-#if UMB_DQ_PIPELINE
-                    const bool early = more && __shfl_sync(0xffffffffu, (int)mbar_try_wait(full_w + dq_st, dq_ph), 0) != 0;
-#else
-                    const bool early = false;
-#endif
-                    if (early) fetch(dq_st);
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full + ts);
-                    if (more && !early) {
+                    if (mine + kDqGroups < n_units) {            // this group's next unit: (dq_st, dq_ph) already point at it
                         mbar_wait(full_w + dq_st, dq_ph);
                         fetch(dq_st);
                     }
@@ -806,32 +758,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const int c_first = whole ? (int)blockIdx.x : sk_owner(tile_u0, U, P);
                 const int c_last = whole ? (int)blockIdx.x : sk_owner(tile_u0 + p.units_per_tile - 1, U, P);
                 const bool reducer = !whole && (int)blockIdx.x == c_first;
-                // Work that does not depend on this segment's own accumulators is done BEFORE waiting for them
-                // (MPAD = 16: one 16-column chunk): the residual rows are fetched and, on the reducing CTA, the
-                // other CTAs' partial sums (published early: they are the first segment of their owners) are
-                // pre-added -- two L2 round trips that otherwise sit on the tail of every launch.
-                float pre[16];
-                __half res_pre[16];
-                bool have_pre = false, have_res = false;
-                if constexpr (MPAD == 16 && UMB_EARLY_REDUCE) {
-                    if ((whole || reducer) && p.mode == UMB_EPI_RESIDUAL && tile * kTileN + fl < p.N_total) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < p.M) res_pre[j] = p.residual[(int64_t)j * p.ld_residual + tile * kTileN + fl];
-                        have_res = true;
-                    }
-                    if (reducer) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pre[j] = 0.f;
-                        reduce_others(pre, 0, tile, c_first, c_last - c_first);
-                        have_pre = true;
-                    }
-                }
-#if UMB_SLEEP_WAIT & 2
-                mbar_wait_sleep<64>(acc_full, seg & 1);          // a whole segment away: do not spin on issue slots
-#else
                 mbar_wait(acc_full, seg & 1);
-#endif
                 tc_fence_after();
                 if (ew == 0 && lane == 0) UMB_TRACE(seg == 0 ? 7 : 12);
                 if (whole) {
@@ -845,7 +772,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                             if (lane == 0) mbar_arrive(acc_empty);
                         }
                         if (m0 < p.M || p.mode == UMB_EPI_SILU_MUL || p.mode == UMB_EPI_ROPE_QKV)
-                            epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch, have_res ? res_pre : nullptr);
+                            epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
                     }
                 } else {
                     // Partial tile.  The CTA that owns the HEAD of the tile (c_first; that part is the last
@@ -885,13 +812,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                                 if (lane == 0) mbar_arrive(acc_empty);
                             }
                             if (!(m0 < p.M || p.mode == UMB_EPI_SILU_MUL || p.mode == UMB_EPI_ROPE_QKV)) continue;
-                            if (have_pre) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] += pre[j];
-                            } else {
-                                reduce_others(v, m0, tile, c_first, n_other);
-                            }
-                            epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch, have_res ? res_pre : nullptr);
+                            reduce_others(v, m0, tile, c_first, n_other);
+                            epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
                         }
                     }
                 }
