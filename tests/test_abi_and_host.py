@@ -90,3 +90,30 @@ def test_reference_import_paths():
     from umbrella.speculation.static_speculation_engine import StaticSpeculationEngine  # noqa: F401
     import umbrella_b200
     assert umbrella.speculation.auto_engine.AutoEngine is umbrella_b200.speculation.auto_engine.AutoEngine
+
+
+def test_scripted_acceptance_reproduces_expected_accept_length():
+    """The benchmark's acceptance script (DEFAULT_ACC per child rank) fed through the oracle's accept block gives
+    the analytic expectation of the tree (3.364 tokens per verify for sequoia_tree-3x4) -- the number bench.py
+    reports as config.expected_accept_len."""
+    import numpy as np
+    import torch
+    from oracle import tree as otree
+    from umbrella_b200.sequoia_utils import expected_accept_length, load_growmap
+    from umbrella_b200.speculation.scripted import ScriptedAcceptance
+    gm = load_growmap("sequoia_tree-3x4.json")
+    succ, N = gm["Successors"], gm["size"]
+    parents = otree.successors_to_parents(succ)
+    mask = np.asarray(gm["mask"], dtype=bool)
+    iters = 4000
+    script = ScriptedAcceptance(succ, seed=11, max_iters=iters, device="cpu")
+    spec = np.arange(100, 100 + N, dtype=np.int64)              # distinct draft tokens per node
+    total = 0
+    for it in range(iters):
+        row = script.choice[it].numpy()
+        sampled = np.where(row >= 0, spec[np.clip(row, 0, None)], -1)   # -1 matches no child
+        path, _ = otree.tree_accept(sampled, spec.copy(), parents, mask, mask.sum(-1))
+        total += len(path)
+    want = expected_accept_length(gm)
+    assert abs(want - 3.3645) < 1e-3
+    assert abs(total / iters - want) < 0.06
