@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from umbrella_b200 import ops, _lib
 DEV = "cuda:0"
 NAMES = ["entry", "setup", "w_issued", "dep_ok", "rec0_landed", "mma0", "mma_end", "acc0", "epi0_done", "exit",
-         "prod_end", "epi_dep_ok", "acc1", "epi1_done"]
+         "prod_end", "epi_dep_ok", "acc1", "epi1_done", "red_acc_loaded", "red_reduced"]
 
 def trace(label, launch, warm=3):
     for _ in range(warm):

@@ -211,6 +211,7 @@ struct GemmParams {
     const __half* bias;
     const __half* residual;
     int64_t ld_residual;
+    int vec_ok;                    // y (and the residual) can be accessed with 16-byte vectors
     unsigned long long* argmax;
     int* counters;                 // [tiles]
     float* slots;                  // [tiles + grid][MPAD][128]
@@ -297,10 +298,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
         const int D = r.head_dim, half_d = D >> 1;
         const bool n_ok = n < p.N_total;
         __half h[16];
+        const bool has_bias = p.bias != nullptr && n_ok;
+        const __half qb = has_bias ? p.bias[n] : __float2half_rn(0.f);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             h[j] = __float2half_rn(v[j]);
-            if (p.bias && n_ok) h[j] = __hadd(h[j], p.bias[n]);
+            if (has_bias) h[j] = __hadd(h[j], qb);
             exch[j * kTileN + fl] = h[j];
         }
         named_bar_sync(2, 128);
@@ -338,8 +341,52 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
         return;
     }
     const bool n_ok = n < p.N_total;
-    if (!n_ok && !(p.mode == UMB_EPI_LOGITS && p.argmax)) return;
     const int mcols = p.M - m0;                       // valid token columns of this chunk (may exceed 16)
+    // fp16 outputs (plain store / residual add): the 16 x 128 tile goes through shared memory so that global memory
+    // is touched with two independent 16-byte accesses per thread instead of one 2-byte access per token row.
+    // Written as the plain per-row loop the residual loads compile into 13 serialised L2 round trips (4.2 us on the
+    // tail of every o-proj / down-proj launch) and the stores into ~500 dependent instructions
+    // (profiles/r1_gemm_tail_trace.txt).  y may alias the residual: all loads of the tile complete before any store.
+    if ((p.mode == UMB_EPI_STORE || p.mode == UMB_EPI_RESIDUAL) && p.vec_ok) {
+        const bool resid = p.mode == UMB_EPI_RESIDUAL;
+        int row[2], col[2];
+        bool ok[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = fl + i * 128;
+            row[i] = idx >> 4;
+            col[i] = (idx & 15) * 8;
+            ok[i] = row[i] < mcols && tile * kTileN + col[i] + 8 <= p.N_total;
+        }
+        if (resid) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (ok[i])
+                    *reinterpret_cast<uint4*>(exch + row[i] * kTileN + col[i]) = *reinterpret_cast<const uint4*>(
+                        p.residual + (int64_t)(m0 + row[i]) * p.ld_residual + tile * kTileN + col[i]);
+            named_bar_sync(2, 128);
+        }
+        const __half bb = (p.bias && n_ok) ? p.bias[n] : __float2half_rn(0.f);
+        __half h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            h[j] = __float2half_rn(v[j]);
+            if (p.bias) h[j] = __hadd(h[j], bb);
+            if (resid) h[j] = __hadd(exch[j * kTileN + fl], h[j]);
+        }
+        if (resid) named_bar_sync(2, 128);            // every thread has read its residual column
+#pragma unroll
+        for (int j = 0; j < 16; ++j) exch[j * kTileN + fl] = h[j];
+        named_bar_sync(2, 128);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (ok[i])
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y) + (int64_t)(m0 + row[i]) * p.ldy + tile * kTileN + col[i]) =
+                    *reinterpret_cast<const uint4*>(exch + row[i] * kTileN + col[i]);
+        named_bar_sync(2, 128);                       // the staging tile is free for the next chunk
+        return;
+    }
+    if (!n_ok && !(p.mode == UMB_EPI_LOGITS && p.argmax)) return;
     const __half b = (p.bias && n_ok) ? p.bias[n] : __float2half_rn(0.f);
     // residual rows first, all loads in flight together: y may alias residual, so a load placed after a
     // store of the previous row would be serialised behind it (one L2 round trip per token row)
@@ -812,7 +859,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                                 if (lane == 0) mbar_arrive(acc_empty);
                             }
                             if (!(m0 < p.M || p.mode == UMB_EPI_SILU_MUL || p.mode == UMB_EPI_ROPE_QKV)) continue;
+                            if (ew == 0 && lane == 0 && m0 == 0) UMB_TRACE(14);
                             reduce_others(v, m0, tile, c_first, n_other);
+                            if (ew == 0 && lane == 0 && m0 == 0) UMB_TRACE(15);
                             epilogue_chunk<MPAD>(p, tile, fl, m0, v, s_exch);
                         }
                     }
@@ -1083,6 +1132,8 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
         UMB_CHECK_ARG(N_total == (r.num_q_heads + 2 * r.num_kv_heads) * r.head_dim);
     }
     if (p.mode == UMB_EPI_RESIDUAL) UMB_CHECK_ARG(p.residual != nullptr);
+    p.vec_ok = (((uintptr_t)y & 15) == 0 && (ldy % 8) == 0 && (N_total % 8) == 0 &&
+                (p.mode != UMB_EPI_RESIDUAL || ((((uintptr_t)p.residual) & 15) == 0 && (p.ld_residual % 8) == 0))) ? 1 : 0;
     if (p.mode == UMB_EPI_SILU_MUL) UMB_CHECK_ARG((N_total % kTileN) == 0 && p.bias == nullptr);
 
     const int mpad = mpad_of(M);
