@@ -267,23 +267,38 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
                                                __half* exch) {
     const int n = tile * kTileN + fl;
     if (p.mode == UMB_EPI_SILU_MUL) {
-        // lanes 64..127 hold `up`, lanes 0..63 hold `gate` of output feature tile*64 + (fl & 63)
-        if (fl >= 64) {
+        // lanes 0..63 hold `gate`, lanes 64..127 `up` of output features tile*64 + (fl & 63).  Both halves of the
+        // 16-row chunk are staged as fp16 (the rounding point of the reference's gate / up tensors), every thread
+        // then finishes 8 of the 16 x 64 outputs in place, and the tile leaves with one 16-byte store per thread.
+        __half* g_t = exch;                    // [16][64] gate, overwritten by the outputs
+        __half* u_t = exch + 16 * 64;          // [16][64] up
+        {
+            __half* dst = (fl < 64 ? g_t : u_t) + (fl & 63);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) exch[(m0 + j) * 64 + (fl - 64)] = __float2half_rn(v[j]);
+            for (int j = 0; j < 16; ++j) dst[j * 64] = __float2half_rn(v[j]);
         }
         named_bar_sync(2, 128);
-        if (fl < 64) {
-            const int no = tile * 64 + fl;
-            if (no < p.N_total / 2) {
+        {
+            const int col = fl & 63, r0 = fl >> 6;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int m = m0 + j;
-                    if (m < p.M) {
-                        const __half g = __float2half_rn(v[j]);
-                        const __half s = __float2half_rn(silu_f(__half2float(g)));
-                        reinterpret_cast<__half*>(p.y)[(int64_t)m * p.ldy + no] = __hmul(s, exch[m * 64 + fl]);
-                    }
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 2 * i;
+                const __half g = g_t[r * 64 + col];
+                const __half sl = __float2half_rn(silu_f(__half2float(g)));
+                g_t[r * 64 + col] = __hmul(sl, u_t[r * 64 + col]);
+            }
+        }
+        named_bar_sync(2, 128);
+        {
+            const int row = fl >> 3, seg = (fl & 7) * 8;
+            const int no = tile * 64 + seg;
+            if (row < p.M - m0 && no + 8 <= p.N_total / 2) {
+                __half* yp = reinterpret_cast<__half*>(p.y) + (int64_t)(m0 + row) * p.ldy + no;
+                if (p.vec_ok) {
+                    *reinterpret_cast<uint4*>(yp) = *reinterpret_cast<const uint4*>(g_t + row * 64 + seg);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) yp[c] = g_t[row * 64 + seg + c];
                 }
             }
         }
