@@ -212,6 +212,7 @@ struct GemmParams {
     const __half* residual;
     int64_t ld_residual;
     int vec_ok;                    // y (and the residual) can be accessed with 16-byte vectors
+    int rope_vec_ok;               // same for q_out / k_cache / v_cache / cos / sin of UMB_EPI_ROPE_QKV
     unsigned long long* argmax;
     int* counters;                 // [tiles]
     float* slots;                  // [tiles + grid][MPAD][128]
@@ -241,7 +242,7 @@ struct GemmCfg {
     static constexpr int kXBytesF16 = MPAD * 128;           // [MPAD][128 B]
     static constexpr int kWBytesF16 = kTileN * 128;         // [128][128 B]
     static constexpr int kPackedStride = 8576;              // record padded to a 128-byte multiple
-    static constexpr int kExchBytes = MPAD * 64 * 2 < 16 * 128 * 2 ? 16 * 128 * 2 : MPAD * 64 * 2;   // SiLU / RoPE exchange
+    static constexpr int kExchBytes = MPAD * 64 * 2 < 3 * 16 * 128 * 2 ? 3 * 16 * 128 * 2 : MPAD * 64 * 2;   // epilogue staging: output tile + cos / sin rows (RoPE)
     // Independent fp32 accumulators in TMEM (columns a * MPAD): consecutive k-steps rotate through them so
     // that back-to-back tcgen05.mma never wait on each other's accumulate (a dependent 128xNx16 MMA chain
     // runs at its ~150-cycle latency, not at its 8-cycle issue rate); the epilogue sums them.
@@ -321,11 +322,69 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int tile, in
             if (has_bias) h[j] = __hadd(h[j], qb);
             exch[j * kTileN + fl] = h[j];
         }
+        const int base = r.n_dev ? r.n_dev[0] : 0;
+        const int mcols = p.M - m0;
+        if (p.rope_vec_ok) {
+            // Staged form: the cos / sin rows of the chunk's 16 positions are fetched with 16-byte loads by the whole
+            // group (two dependent round trips in total instead of three per token through one register), the
+            // rotated tile is finished in shared memory and leaves with two 16-byte stores per thread.
+            __half* cos_t = exch + 16 * kTileN;          // [16][D]
+            __half* sin_t = cos_t + 16 * kTileN;         // [16][D]
+            const int segs = D >> 3;                     // 16-byte segments per table row
+            const int64_t* pid = r.position_ids + (r.n_dev ? base + r.row_offset : 0) + m0;
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int sidx = fl + it * 128;
+                const int row = sidx / segs, seg = sidx - row * segs;
+                if (sidx < 16 * segs && row < mcols) {
+                    const int64_t off = pid[row] * D + seg * 8;
+                    *reinterpret_cast<uint4*>(cos_t + row * D + seg * 8) =
+                        *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(r.cos) + off);
+                    *reinterpret_cast<uint4*>(sin_t + row * D + seg * 8) =
+                        *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(r.sin) + off);
+                }
+            }
+            named_bar_sync(2, 128);
+            const int head = n / D, d = n - head * D;
+            const bool rot = n_ok && head < r.num_q_heads + r.num_kv_heads;
+            __half o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                o[j] = h[j];
+                if (rot && j < mcols) {
+                    const __half pr = exch[j * kTileN + (fl ^ half_d)];
+                    // (x * cos) + (rotate_half(x) * sin): two products and one sum, each rounded (no fma)
+                    o[j] = __hadd_rn(__hmul_rn(h[j], cos_t[j * D + d]), __hmul_rn(d < half_d ? __hneg(pr) : pr, sin_t[j * D + d]));
+                }
+            }
+            named_bar_sync(2, 128);                  // every partner value has been read
+#pragma unroll
+            for (int j = 0; j < 16; ++j) exch[j * kTileN + fl] = o[j];
+            named_bar_sync(2, 128);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int sidx = fl + it * 128, row = sidx >> 4, c0 = (sidx & 15) * 8;
+                const int n0 = tile * kTileN + c0;
+                if (row < mcols && n0 + 8 <= p.N_total) {
+                    const int hd = n0 / D, d0 = n0 - hd * D, m = m0 + row;
+                    __half* dst;
+                    if (hd < r.num_q_heads) {
+                        dst = reinterpret_cast<__half*>(r.q_out) + ((int64_t)m * r.num_q_heads + hd) * D;
+                    } else {
+                        const bool is_k = hd < r.num_q_heads + r.num_kv_heads;
+                        const int kvh = hd - r.num_q_heads - (is_k ? 0 : r.num_kv_heads);
+                        dst = reinterpret_cast<__half*>(is_k ? r.k_cache : r.v_cache) +
+                              (int64_t)(base + r.kv_offset + m) * r.kv_tok_stride + (int64_t)kvh * r.kv_head_stride;
+                    }
+                    *reinterpret_cast<uint4*>(dst + d0) = *reinterpret_cast<const uint4*>(exch + row * kTileN + c0);
+                }
+            }
+            named_bar_sync(2, 128);
+            return;
+        }
         named_bar_sync(2, 128);
         if (n_ok) {
             const int head = n / D, d = n - head * D;
-            const int base = r.n_dev ? r.n_dev[0] : 0;
-            const int mcols = p.M - m0;
             const bool rot = head < r.num_q_heads + r.num_kv_heads;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -1145,6 +1204,8 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
         UMB_CHECK_ARG(r.q_out && r.k_cache && r.v_cache && r.cos && r.sin && r.position_ids);
         UMB_CHECK_ARG((r.head_dim == 64 || r.head_dim == 128) && r.num_q_heads >= 1 && r.num_kv_heads >= 1);
         UMB_CHECK_ARG(N_total == (r.num_q_heads + 2 * r.num_kv_heads) * r.head_dim);
+        const uintptr_t ptrs = (uintptr_t)r.q_out | (uintptr_t)r.k_cache | (uintptr_t)r.v_cache | (uintptr_t)r.cos | (uintptr_t)r.sin;
+        p.rope_vec_ok = ((ptrs & 15) == 0 && (r.kv_tok_stride % 8) == 0 && (r.kv_head_stride % 8) == 0) ? 1 : 0;
     }
     if (p.mode == UMB_EPI_RESIDUAL) UMB_CHECK_ARG(p.residual != nullptr);
     p.vec_ok = (((uintptr_t)y & 15) == 0 && (ldy % 8) == 0 && (N_total % 8) == 0 &&
