@@ -13,6 +13,8 @@
 // The mask is never materialised for the tree case: rows see [0, prefix_len) unconditionally and
 // prefix_len + j iff bit j of their ancestor bitmask is set.  Long contexts are split along KV
 // (grid.z) and merged by a second kernel with a log-sum-exp reduction.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_kernel(const AttnParam
 // in the loop), and merge their (m, l, o) partials through shared memory at the end.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSBN = 32;
+constexpr int kSlabTilesPerCta = 32;     // minimum kv tiles per slab CTA before the KV range is split across CTAs
 
 template <int D>
 __device__ __forceinline__ void load_tile_warp(__half* smem, const __half* gbase, int64_t tok_stride, int row0, int kv_hi,
@@ -724,7 +727,13 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
     const bool slab = !(kv_bound > 8192 && slabs > 2);
     const int ctas_base = (slab ? slabs : (rows_total + kBM - 1) / kBM) * p.Hkv;
     const int kv_tiles = (kv_bound + (slab ? kSBN : kBN) - 1) / (slab ? kSBN : kBN);
-    const int tiles_per_cta_min = slab ? 32 : 4;              // slab CTAs run 4 tiles at a time (one per warp)
+    static int slab_tiles = 0;                                // UMB_ATTN_SLAB_TILES: tuning override (read once)
+    if (slab_tiles == 0) {
+        const char* e = getenv("UMB_ATTN_SLAB_TILES");
+        slab_tiles = e ? atoi(e) : kSlabTilesPerCta;
+        if (slab_tiles < 4) slab_tiles = kSlabTilesPerCta;
+    }
+    const int tiles_per_cta_min = slab ? slab_tiles : 4;      // slab CTAs run 4 tiles at a time (one per warp)
     int splits = (kv_tiles + tiles_per_cta_min - 1) / tiles_per_cta_min;
     const int by_ctas = (2 * sm_count()) / (ctas_base > 0 ? ctas_base : 1);
     splits = splits > by_ctas ? by_ctas : splits;

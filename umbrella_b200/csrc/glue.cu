@@ -61,6 +61,58 @@ rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __hal
     }
 }
 
+// Register-resident form for hidden <= 8 * 256 * VPT: the row and the weight vector are fetched once, all loads in
+// flight together (the weight loads even before griddepcontrol.wait -- they never depend on the predecessor), so
+// the kernel is one global round trip + the block reduction instead of three dependent passes.  Same arithmetic.
+template <int VPT>
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_reg_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int hidden,
+                   float eps) {
+    __shared__ float s_part[kNormThreads / 32];
+    pdl_launch_dependents();
+    const int vecs = hidden >> 3;
+    H8 a[VPT], b[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int v = threadIdx.x + i * kNormThreads;
+        b[i].u = v < vecs ? reinterpret_cast<const uint4*>(w)[v] : make_uint4(0, 0, 0, 0);
+    }
+    pdl_wait();
+    const __half* xr = x + (int64_t)blockIdx.x * hidden;
+    __half* yr = y + (int64_t)blockIdx.x * hidden;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int v = threadIdx.x + i * kNormThreads;
+        a[i].u = v < vecs ? reinterpret_cast<const uint4*>(xr)[v] : make_uint4(0, 0, 0, 0);
+    }
+    // same accumulation order as the streaming kernel: vector by vector, element by element
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float f = __half2float(a[i].h[j]);
+            ss = fmaf(f, f, ss);
+        }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kNormThreads / 32; ++i) tot += s_part[i];
+    const float r = rsqrtf(tot / (float)hidden + eps);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int v = threadIdx.x + i * kNormThreads;
+        if (v < vecs) {
+            H8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.h[j] = __float2half_rn(__half2float(a[i].h[j]) * r * __half2float(b[i].h[j]));
+            reinterpret_cast<uint4*>(yr)[v] = o.u;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // elementwise
 // ------------------------------------------------------------------------------------------------
@@ -194,8 +246,20 @@ extern "C" int umb_rmsnorm_f16(const void* x, const void* weight, void* y, int r
                                umb_stream_t stream) {
     UMB_CHECK_ARG(x && weight && y && rows >= 1 && hidden >= 8 && (hidden % 8) == 0);
     UMB_CHECK_ARG((((uintptr_t)x | (uintptr_t)weight | (uintptr_t)y) & 15) == 0);
-    UMB_LAUNCH_PDL(rmsnorm_kernel, dim3(rows), dim3(kNormThreads), 0, (cudaStream_t)stream, (const __half*)x,
-                   (const __half*)weight, (__half*)y, hidden, eps);
+    const int vecs = hidden >> 3;
+    cudaStream_t st = (cudaStream_t)stream;
+    const __half* xh = (const __half*)x;
+    const __half* wh = (const __half*)weight;
+    __half* yh = (__half*)y;
+    if (vecs <= kNormThreads) {
+        UMB_LAUNCH_PDL(rmsnorm_reg_kernel<1>, dim3(rows), dim3(kNormThreads), 0, st, xh, wh, yh, hidden, eps);
+    } else if (vecs <= 2 * kNormThreads) {
+        UMB_LAUNCH_PDL(rmsnorm_reg_kernel<2>, dim3(rows), dim3(kNormThreads), 0, st, xh, wh, yh, hidden, eps);
+    } else if (vecs <= 4 * kNormThreads) {
+        UMB_LAUNCH_PDL(rmsnorm_reg_kernel<4>, dim3(rows), dim3(kNormThreads), 0, st, xh, wh, yh, hidden, eps);
+    } else {
+        UMB_LAUNCH_PDL(rmsnorm_kernel, dim3(rows), dim3(kNormThreads), 0, st, xh, wh, yh, hidden, eps);
+    }
     count_launches(1);
     return UMB_OK;
 }
