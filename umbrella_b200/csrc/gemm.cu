@@ -1217,7 +1217,12 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     if (U >= (1ll << 31)) return UMB_ERR_UNSUPPORTED;
     int grid = sm_count();
     if ((long long)grid > U) grid = (int)U;
-    if (U < 16ll * grid && p.tiles <= grid) {
+    static int aligned_split = -1;                   // UMB_GEMM_ALIGNED_SPLIT=0: plain stream-K for small problems too (tuning)
+    if (aligned_split < 0) {
+        const char* e = getenv("UMB_GEMM_ALIGNED_SPLIT");
+        aligned_split = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (aligned_split && U < 16ll * grid && p.tiles <= grid) {
         // small problem (draft-model linears): latency-bound, so cut every tile into the same power-of-two
         // number of k-slices (one segment per CTA, fewer partials per tile to reduce) instead of balancing units
         int S = 1;
