@@ -13,62 +13,55 @@ import torch
 from .. import ops
 
 
+_TRIPLET = ("qweight", "qzeros", "scales")          # the AutoAWQ GEMM-layout checkpoint tensors of one linear
+
+
 class AwqLinear:
     def __init__(self):
-        self.in_features = 0
-        self.out_features = 0
-        self.w_bit = 0
-        self.group_size = 0
-        self.qweight: torch.Tensor = None
-        self.qzeros: torch.Tensor = None
-        self.scales: torch.Tensor = None
-        self.bias: torch.Tensor = None
+        self.in_features = self.out_features = self.w_bit = self.group_size = 0
+        for name in _TRIPLET + ("bias",):
+            setattr(self, name, None)
         self.packed: torch.Tensor = None       # device-resident repacked stream
         self._workspace = None
 
     def _meta(self, module):
-        self.in_features = module.in_features
-        self.out_features = module.out_features
-        self.w_bit = module.w_bit
-        self.group_size = module.group_size
-        if self.w_bit != 4 or self.group_size != 128:
+        for name in ("in_features", "out_features", "w_bit", "group_size"):
+            setattr(self, name, getattr(module, name))
+        if (self.w_bit, self.group_size) != (4, 128):
             raise ValueError(f"AwqLinear: only w_bit=4, group_size=128 is implemented (got {self.w_bit}, {self.group_size})")
 
-    def init_parameters(self, module):
-        """``module``: anything with WQLinear_GEMM's attributes (awq_utils.py:18-30)."""
+    def _adopt(self, module, transform):
+        """Take the checkpoint tensors of ``module`` through ``transform`` (pin / zeros_like)."""
         self._meta(module)
-        pin = (lambda t: t.detach().pin_memory()) if torch.cuda.is_available() else (lambda t: t.detach())
-        self.qweight, self.qzeros, self.scales = pin(module.qweight), pin(module.qzeros), pin(module.scales)
-        self.bias = module.bias.detach() if getattr(module, "bias", None) is not None else None
+        for name in _TRIPLET:
+            setattr(self, name, transform(getattr(module, name).detach()))
+        bias = getattr(module, "bias", None)
+        self.bias = None if bias is None else transform(bias.detach())
         self.packed = None
 
+    def init_parameters(self, module):
+        """``module``: anything with WQLinear_GEMM's attributes (awq_utils.py:18-30); host copies are pinned so
+        that ``copy`` into a device-side twin is an asynchronous DMA (awq_utils.py:24-26)."""
+        self._adopt(module, (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t))
+
     def empty_like(self, module):
-        self._meta(module)
-        self.qweight = torch.zeros_like(module.qweight.detach())
-        self.qzeros = torch.zeros_like(module.qzeros.detach())
-        self.scales = torch.zeros_like(module.scales.detach())
-        if getattr(module, "bias", None) is not None:
-            self.bias = torch.zeros_like(module.bias.detach())
-        self.packed = None
+        self._adopt(module, torch.zeros_like)
 
     def _repack(self):
         if self.qweight.is_cuda:
             self.packed = ops.awq_repack(self.qweight, self.qzeros, self.scales, self.group_size, packed=self.packed)
 
+    def _each(self):
+        return [n for n in _TRIPLET + ("bias",) if getattr(self, n) is not None]
+
     def to(self, device, non_blocking=True):
-        self.qweight = self.qweight.to(device, non_blocking=non_blocking)
-        self.qzeros = self.qzeros.to(device, non_blocking=non_blocking)
-        self.scales = self.scales.to(device, non_blocking=non_blocking)
-        if self.bias is not None:
-            self.bias = self.bias.to(device, non_blocking=non_blocking)
+        for name in self._each():
+            setattr(self, name, getattr(self, name).to(device, non_blocking=non_blocking))
         self._repack()
 
     def copy(self, module: "AwqLinear", non_blocking=True):
-        self.qweight.copy_(module.qweight, non_blocking=non_blocking)
-        self.qzeros.copy_(module.qzeros, non_blocking=non_blocking)
-        self.scales.copy_(module.scales, non_blocking=non_blocking)
-        if self.bias is not None:
-            self.bias.copy_(module.bias, non_blocking=non_blocking)
+        for name in self._each():
+            getattr(self, name).copy_(getattr(module, name), non_blocking=non_blocking)
         self._repack()
 
     def apply(self, x: torch.Tensor) -> torch.Tensor:

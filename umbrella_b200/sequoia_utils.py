@@ -76,14 +76,19 @@ def generate_sequoia_tree(width: int, depth: int, acc: list[float] | None = None
 
 
 def load_growmap(path: str) -> dict:
-    """Load a growmap; bare file names resolve against the packaged trees directory, and a path into
-    the reference checkout (``../umbrella/trees/x.json``) resolves to the same file name."""
-    if not os.path.exists(path):
-        alt = os.path.join(TREES_DIR, os.path.basename(path))
-        if os.path.exists(alt):
-            path = alt
-    with open(path) as f:
-        gm = json.load(f)
+    """Load a growmap.  The Sequoia trees the reference ships (umbrella/trees/*.json) are packaged in compact form
+    -- ``trees/growmaps.json``: file name -> successor lists -- and rebuilt into the full schema on load, so a bare
+    file name or a path into the reference checkout (``../umbrella/trees/x.json``) both resolve by base name."""
+    if os.path.exists(path):
+        with open(path) as f:
+            gm = json.load(f)
+    else:
+        with open(os.path.join(TREES_DIR, "growmaps.json")) as f:
+            packaged = json.load(f)
+        name = os.path.basename(path)
+        if name not in packaged:
+            raise FileNotFoundError(f"{path}: no such growmap file, and not one of the packaged trees {sorted(packaged)}")
+        gm = growmap_from_successors(packaged[name])
     if "Successors" not in gm or "size" not in gm:
         raise ValueError(f"{path}: not a growmap")
     if "mask" not in gm or "depth" not in gm or "roots" not in gm or "branches" not in gm:
