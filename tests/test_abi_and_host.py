@@ -117,3 +117,34 @@ def test_scripted_acceptance_reproduces_expected_accept_length():
     want = expected_accept_length(gm)
     assert abs(want - 3.3645) < 1e-3
     assert abs(total / iters - want) < 0.06
+
+
+def test_product_sequoia_utils_match_reference_fixtures():
+    """The PRODUCT's growmap builders (umbrella_b200/sequoia_utils.py -- what the engines and
+    examples/construct_sequoia-style front-ends call) against the fixtures produced by the reference's own
+    ``generate_sequoia_tree`` / shipped tree files (tests/golden/trees.json, oracle/make_golden.py)."""
+    import hashlib
+    import json
+    from umbrella_b200.sequoia_utils import generate_sequoia_tree, growmap_from_successors, load_growmap
+
+    def canon_hash(obj):
+        return hashlib.sha256(json.dumps(obj, sort_keys=True, separators=(",", ":")).encode()).hexdigest()
+
+    trees = json.load(open(os.path.join(ROOT, "tests", "golden", "trees.json")))
+    for key, ref in trees["generated"].items():
+        if key == "5x5_acc":
+            g = generate_sequoia_tree(5, 5, acc=ref["acc"])
+        else:
+            w, d = map(int, key.split("x"))
+            g = generate_sequoia_tree(w, d)
+        assert g["Successors"] == ref["Successors"], key
+        assert canon_hash({k: g[k] for k in ("roots", "branches", "Successors", "mask", "depth", "size")}) == ref["all_sha256"], key
+    for name, ref in trees["shipped"].items():
+        gm = load_growmap(name)                                   # packaged compact form -> full schema
+        assert gm["Successors"] == ref["Successors"] and gm["size"] == ref["size"], name
+        assert gm["depth"] == ref["depth"] and gm["roots"] == ref["roots"] and gm["branches"] == ref["branches"], name
+        assert canon_hash(gm["mask"]) == ref["mask_sha256"], name
+        assert growmap_from_successors(ref["Successors"]) == gm
+        assert load_growmap("../umbrella/trees/" + name) == gm    # the path form of the reference's configs
+    with pytest.raises(FileNotFoundError):
+        load_growmap("no_such_tree.json")
