@@ -173,15 +173,17 @@ int umb_rope_append_f16(const void* qkv, int64_t ld_qkv, void* q_out, void* k_ca
  * ---------------------------------------------------------------------------------------------- */
 /* In:  sampled int64[N] (target token after each node), tokens int64[S], position_ids int64[S],
  *      parents int32[N] (parents[0] = 0, parent < child), depth int32[N], num_nodes (or
- *      state[0] if state != NULL), eos int64[n_eos].
+ *      state[0] if state != NULL), capacity = elements of tokens / position_ids (no access at or past
+ *      it: a prefix that leaves no room for the tree is clamped instead of corrupting memory; the
+ *      engines refuse such a state on the host), eos int64[n_eos].
  * Out: tokens[n : n+len+1], position_ids updated exactly as the reference's verify() does;
  *      result int32[4 + N]: {accept_len, continue, new_num_nodes, bonus_lo32, path_abs[0..len)}
  *      (device or mapped-pinned memory); if state != NULL (device int32[4]): state[0] = new_num_nodes,
  *      state[1] = new_num_nodes + N, state[2] = the num_nodes this call started from (the gather
  *      offset: pass &state[2] as umb_kv_gather's offset_dev). */
 int umb_tree_accept(const int64_t* sampled, int64_t* tokens, int64_t* position_ids, const int32_t* parents,
-                    const int32_t* depth, int N, int num_nodes, int32_t* state, const int64_t* eos, int n_eos,
-                    int32_t* result, umb_stream_t stream);
+                    const int32_t* depth, int N, int num_nodes, int capacity, int32_t* state, const int64_t* eos,
+                    int n_eos, int32_t* result, umb_stream_t stream);
 
 /* cache[plane, offset + j, :] = cache[plane, path[j], :] for j < len, for every plane
  * (plane = layer for [L,S,Hkv,D]; layer*head for [L,Hkv,S,D]); K and V in one launch.
@@ -201,7 +203,7 @@ int umb_kv_gather(void* k_cache, void* v_cache, int num_planes, int64_t plane_st
  *   tree_bits[id, :] = tree_bits[parent, :] | bit id.
  * n = n_dev[0] if n_dev != NULL (device int32) else num_nodes.  rows <= 128, rows * beams <= 4096. */
 int umb_dyn_tree_expand(const float* topk_logits, const int64_t* topk_ids, int rows, int beams, int width,
-                        int level_first, int num_nodes, const int32_t* n_dev, float* tree_score, int64_t* tokens,
+                        int level_first, int num_nodes, int capacity, const int32_t* n_dev, float* tree_score, int64_t* tokens,
                         int32_t* parents, uint32_t* tree_bits, int tree_words, umb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -311,7 +313,7 @@ int umb_llama_forward_dyn(const umb_llama_t* model, const int64_t* tokens_base, 
 
 /* tokens_base[n_dev[0] + offset + i] = src[i], i < count  (draft tokens of the next tree level) */
 int umb_store_tokens(int64_t* tokens_base, const int32_t* n_dev, int offset, const int64_t* src, int count,
-                     umb_stream_t stream);
+                     int capacity, umb_stream_t stream);
 
 #ifdef __cplusplus
 }

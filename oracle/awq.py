@@ -116,3 +116,18 @@ def random_awq(k: int, n: int, group: int, rng: np.random.Generator, scale: floa
     qz = rng.integers(0, 16, size=(k // group, n), dtype=np.int64)
     sc = (scale * (0.5 + rng.random((k // group, n)))).astype(np.float16)
     return pack_cols_awq(qw), pack_cols_awq(qz), sc
+
+
+def dequantize_torch(qweight, qzeros, scales, group: int, exact: bool = False):
+    """Device-agnostic torch twin of ``dequantize`` (same nibble order): fp32 [K, N] holding either the
+    fp16-rounded weights fp16((q - z) * s) -- what both upstream kernels feed their MMAs -- or, with
+    ``exact=True``, the unrounded product (exact in fp32: a 5-bit integer times an 11-bit mantissa).
+    Used where the numpy version is too slow (70B-shape parity tests run the oracle on the GPU box)."""
+    import torch
+    shifts = torch.tensor([4 * int(p) for p in AWQ_NIBBLE_OF_COL], dtype=torch.int32, device=qweight.device)
+    q = ((qweight.unsqueeze(-1) >> shifts) & 0xF).reshape(qweight.shape[0], -1)            # [K, N]
+    z = ((qzeros.unsqueeze(-1) >> shifts) & 0xF).reshape(qzeros.shape[0], -1)              # [K/g, N]
+    k = q.shape[0]
+    d = (q - z.repeat_interleave(group, dim=0)[:k]).to(torch.float32)
+    w = d * scales.to(torch.float32).repeat_interleave(group, dim=0)[:k]
+    return w if exact else w.to(torch.float16).to(torch.float32)

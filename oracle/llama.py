@@ -166,6 +166,71 @@ def dequant_fp16(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tens
     return torch.from_numpy(w)
 
 
+
+# --------------------------------------------------------------------------------------
+# one decoder layer, functional and device-agnostic (the 70B-shape parity tests stream the layers
+# through it on the GPU box; OracleLlama below calls it with its own caches)
+# --------------------------------------------------------------------------------------
+def _linear(x16: torch.Tensor, w32: torch.Tensor) -> torch.Tensor:
+    return (x16.float() @ w32).to(torch.float16)
+
+
+def masked_attention(shape: LlamaShape, q, k_layer, v_layer, kv_len: int, mask):
+    """cache.py:67-87 with the pure-torch arithmetic of cache.py:169-192: masked GQA attention over rows
+    [0, kv_len) of one layer's cache, fp32 softmax, fp16 out.  q: [1, n, Hq, D] fp16; mask: bool [n, >= kv_len]."""
+    n_new = q.shape[1]
+    kk = k_layer[:kv_len].float()                          # [kv, Hkv, D]
+    vv = v_layer[:kv_len].float()
+    hq, hkv = shape.num_attention_heads, shape.num_key_value_heads
+    g = hq // hkv
+    qq = q[0].float().reshape(n_new, hkv, g, -1)           # [q, Hkv, g, D]
+    s = torch.einsum("qhgd,khd->hgqk", qq, kk) / math.sqrt(shape.head_dim)
+    s = s.masked_fill(~mask[:, :kv_len][None, None], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("hgqk,khd->qhgd", p, vv)
+    return o.reshape(1, n_new, hq * shape.head_dim).to(torch.float16)
+
+
+def layer_forward(shape: LlamaShape, w: dict, hidden, position_ids, attention_mask, k_layer, v_layer, kv_before: int,
+                  cos_cache, sin_cache):
+    """llama.py:262-303.  ``w``: fp32 [K, N] matrices per linear + the two fp16 norm vectors; ``k_layer`` /
+    ``v_layer``: this layer's cache [S, Hkv, D] fp16, the new rows are appended at ``kv_before``."""
+    sh = shape
+    bsz, q_len, _ = hidden.shape
+    residual = hidden
+    x = rmsnorm(hidden, w["input_layernorm"], sh.rms_norm_eps)
+    q = _linear(x, w["wq"]).view(bsz, q_len, sh.num_attention_heads, sh.head_dim)
+    k = _linear(x, w["wk"]).view(bsz, q_len, sh.num_key_value_heads, sh.head_dim)
+    v = _linear(x, w["wv"]).view(bsz, q_len, sh.num_key_value_heads, sh.head_dim)
+    q, k = apply_rope(q, k, cos_cache, sin_cache, position_ids)
+    k_layer[kv_before:kv_before + q_len] = k[0]
+    v_layer[kv_before:kv_before + q_len] = v[0]
+    a = masked_attention(sh, q, k_layer, v_layer, kv_before + q_len, attention_mask)
+    hidden = residual + _linear(a, w["wo"])
+    residual = hidden
+    x = rmsnorm(hidden, w["post_attention_layernorm"], sh.rms_norm_eps)
+    up = _linear(x, w["up_proj"])
+    gate = torch.nn.functional.silu(_linear(x, w["gate_proj"]).float()).to(torch.float16)
+    hidden = residual + _linear(gate * up, w["down_proj"])
+    return hidden
+
+
+def final_logits(shape: LlamaShape, hidden, norm_weight, lm_head):
+    """llama.py:316-322: final RMSNorm, fp16 lm_head GEMM output cast to float."""
+    hidden = rmsnorm(hidden, norm_weight, shape.rms_norm_eps)
+    return (hidden.float() @ lm_head.float().t()).to(torch.float16).float()
+
+
+def oracle_layer_weights(raw: dict, group: int, awq: bool, exact: bool = False) -> dict:
+    """raw synth_layer() tensors (any device) -> fp32 [K, N] matrices + norm vectors for layer_forward."""
+    d = {}
+    for name in LINEAR_NAMES:
+        d[name] = awq_oracle.dequantize_torch(*raw[name], group, exact=exact) if awq else raw[name].t().float().contiguous()
+    d["input_layernorm"] = raw["input_layernorm"]
+    d["post_attention_layernorm"] = raw["post_attention_layernorm"]
+    return d
+
+
 # --------------------------------------------------------------------------------------
 # the model
 # --------------------------------------------------------------------------------------
@@ -220,47 +285,13 @@ class OracleLlama:
         self.v_cache[:, offset + m:] = 0.0
         self.kv_offset = offset + m
 
-    @staticmethod
-    def _linear(x16: torch.Tensor, w32: torch.Tensor) -> torch.Tensor:
-        return (x16.float() @ w32).to(torch.float16)
-
-    def _attention(self, q, k, v, layer_idx, n_new, mask):
-        """cache.py:53-87 (append + masked GQA attention, fp32 softmax, fp16 out)."""
+    def layer_compute(self, w, layer_idx, hidden, position_ids, attention_mask):
+        """llama.py:262-303 (append at kv_offset: cache.py:53-65)."""
+        n_new = hidden.shape[1]
         if layer_idx == 0:
             self.kv_offset += n_new
-        off = self.kv_offset
-        self.k_cache[layer_idx, off - n_new:off] = k[0]
-        self.v_cache[layer_idx, off - n_new:off] = v[0]
-        kk = self.k_cache[layer_idx, :off].float()            # [kv, Hkv, D]
-        vv = self.v_cache[layer_idx, :off].float()
-        hq, hkv = self.shape.num_attention_heads, self.shape.num_key_value_heads
-        g = hq // hkv
-        qq = q[0].float().reshape(n_new, hkv, g, -1)          # [q, Hkv, g, D]
-        s = torch.einsum("qhgd,khd->hgqk", qq, kk) / math.sqrt(self.shape.head_dim)
-        m = mask[:, :off]
-        s = s.masked_fill(~m[None, None], float("-inf"))
-        p = torch.softmax(s, dim=-1)
-        o = torch.einsum("hgqk,khd->qhgd", p, vv)
-        return o.reshape(1, n_new, hq * self.shape.head_dim).to(torch.float16)
-
-    def layer_compute(self, w, layer_idx, hidden, position_ids, attention_mask):
-        """llama.py:262-303."""
-        sh = self.shape
-        bsz, q_len, _ = hidden.shape
-        residual = hidden
-        x = rmsnorm(hidden, w["input_layernorm"], sh.rms_norm_eps)
-        q = self._linear(x, w["wq"]).view(bsz, q_len, sh.num_attention_heads, sh.head_dim)
-        k = self._linear(x, w["wk"]).view(bsz, q_len, sh.num_key_value_heads, sh.head_dim)
-        v = self._linear(x, w["wv"]).view(bsz, q_len, sh.num_key_value_heads, sh.head_dim)
-        q, k = apply_rope(q, k, self.cos_cache, self.sin_cache, position_ids)
-        a = self._attention(q, k, v, layer_idx, q_len, attention_mask)
-        hidden = residual + self._linear(a, w["wo"])
-        residual = hidden
-        x = rmsnorm(hidden, w["post_attention_layernorm"], sh.rms_norm_eps)
-        up = self._linear(x, w["up_proj"])
-        gate = torch.nn.functional.silu(self._linear(x, w["gate_proj"]).float()).to(torch.float16)
-        hidden = residual + self._linear(gate * up, w["down_proj"])
-        return hidden
+        return layer_forward(self.shape, w, hidden, position_ids, attention_mask, self.k_cache[layer_idx],
+                             self.v_cache[layer_idx], self.kv_offset - n_new, self.cos_cache, self.sin_cache)
 
     @torch.inference_mode()
     def inference(self, input_ids, position_ids, attention_mask, storage_ids=None):
@@ -268,6 +299,4 @@ class OracleLlama:
         hidden = torch.nn.functional.embedding(input_ids, self.embed_tokens)
         for idx in range(self.num_layers):
             hidden = self.layer_compute(self.layers[idx], idx, hidden, position_ids, attention_mask)
-        hidden = rmsnorm(hidden, self.norm_weight, self.shape.rms_norm_eps)
-        logits = (hidden.float() @ self.lm_head.float().t()).to(torch.float16).float()
-        return logits
+        return final_logits(self.shape, hidden, self.norm_weight, self.lm_head)

@@ -1,0 +1,101 @@
+"""The reference's OWN GPU kernels, op by op -- the second comparator of the forward parity tests.
+
+TEST INFRASTRUCTURE ONLY (GPU box).  The reference forward (umbrella/models/llama.py:262-322) is plain
+torch glue around three third-party kernels; this module restates that glue and calls the same kernels:
+
+  * ``AwqLinear.apply`` (umbrella/quantization/awq_utils.py:63-86) -> ``awq_ext.gemm_forward_cuda(x, qweight,
+    scales, qzeros, 8)``.  ``awq_ext`` (autoawq-kernels 0.0.8) is absent from the image; vLLM 0.22 ships a build
+    of the same upstream CUDA source behind ``vllm._custom_ops.awq_gemm`` (same argument order, split_k_iters = 8).
+  * ``layer_norm`` (umbrella/models/model_utils.py:54-64) -> ``flashinfer.rmsnorm``.
+  * ``KV_Cache.compute_attention`` (umbrella/attn/cache.py:67-87) -> ``flashinfer.single_prefill_with_kv_cache(
+    q, k, v, kv_layout="NHD", custom_mask=mask, allow_fp16_qk_reduction=True)``.  The kwarg is called
+    ``use_fp16_qk_reduction`` in flashinfer 0.6.11, and this image's flashinfer cannot build the fp16-reduction
+    variant at all (static_assert "install boost_math", prefill.cuh:182), so the fp32-reduction kernel -- the more
+    accurate one -- stands in; this is stated wherever the numbers are quoted.
+  * RoPE, SiLU, residual adds, lm_head: the reference's own torch fp16 ops, restated verbatim.
+
+flashinfer JIT-compiles its modules; they are pre-built for sm_100a into baseline/fi_ws (git-ignored, travels to
+the GPU box) by scripts/build_flashinfer_modules.py, and FLASHINFER_WORKSPACE_BASE points there.
+"""
+from __future__ import annotations
+
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("FLASHINFER_WORKSPACE_BASE", os.path.join(ROOT, "baseline", "fi_ws"))
+os.environ.setdefault("FLASHINFER_CUDA_ARCH_LIST", "10.0a")
+os.environ.setdefault("VLLM_USE_TRITON_AWQ", "0")
+
+import torch
+
+
+def available() -> str | None:
+    """None when the kernels can be called, else the reason."""
+    try:
+        import flashinfer  # noqa: F401
+        from vllm import _custom_ops  # noqa: F401
+        if not hasattr(torch.ops._C, "awq_gemm"):
+            return "vLLM _C.awq_gemm missing"
+    except Exception as e:  # pragma: no cover
+        return repr(e)
+    return None
+
+
+def awq_linear(x: torch.Tensor, triplet) -> torch.Tensor:
+    """AwqLinear.apply for fewer than 1024 rows (awq_utils.py:74-77)."""
+    from vllm import _custom_ops as vops
+    qweight, qzeros, scales = triplet
+    return vops.awq_gemm(x.reshape(-1, x.shape[-1]).contiguous(), qweight, scales, qzeros, 8)
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    import flashinfer
+    return flashinfer.rmsnorm(x.contiguous(), w, eps)
+
+
+def rotate_half(x):
+    x1 = x[..., : x.shape[-1] // 2]
+    x2 = x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rotary_pos_emb(q, k, cos, sin, position_ids):
+    """model_utils.py:24-52 on [n, H, D] tensors (unsqueeze_dim = the head axis)."""
+    c = cos[position_ids].unsqueeze(1)
+    s = sin[position_ids].unsqueeze(1)
+    return (q * c) + (rotate_half(q) * s), (k * c) + (rotate_half(k) * s)
+
+
+def attention(q, k, v, mask) -> torch.Tensor:
+    """cache.py:77-85.  q [n, Hq, D], k / v [kv, Hkv, D] fp16, mask bool [n, kv]."""
+    import flashinfer
+    return flashinfer.single_prefill_with_kv_cache(q.contiguous(), k.contiguous(), v.contiguous(), kv_layout="NHD",
+                                                   custom_mask=mask.contiguous(), use_fp16_qk_reduction=False)
+
+
+def layer_forward(shape, raw: dict, hidden, position_ids, mask, k_layer, v_layer, kv_before: int, cos, sin):
+    """LlamaAwq.layer_compute (llama.py:262-303) over the raw AWQ triplets of one layer.  hidden: [n, H] fp16."""
+    n = hidden.shape[0]
+    hq, hkv, d = shape.num_attention_heads, shape.num_key_value_heads, shape.head_dim
+    residual = hidden
+    x = rmsnorm(hidden, raw["input_layernorm"], shape.rms_norm_eps)
+    q = awq_linear(x, raw["wq"]).view(n, hq, d)
+    k = awq_linear(x, raw["wk"]).view(n, hkv, d)
+    v = awq_linear(x, raw["wv"]).view(n, hkv, d)
+    q, k = apply_rotary_pos_emb(q, k, cos, sin, position_ids)
+    k_layer[kv_before:kv_before + n] = k
+    v_layer[kv_before:kv_before + n] = v
+    kv = kv_before + n
+    a = attention(q, k_layer[:kv], v_layer[:kv], mask[:, :kv]).reshape(n, hq * d)
+    hidden = residual + awq_linear(a, raw["wo"])
+    residual = hidden
+    x = rmsnorm(hidden, raw["post_attention_layernorm"], shape.rms_norm_eps)
+    up = awq_linear(x, raw["up_proj"])
+    gate = torch.nn.functional.silu(awq_linear(x, raw["gate_proj"]))
+    hidden = residual + awq_linear(gate * up, raw["down_proj"])
+    return hidden
+
+
+def final_logits(shape, hidden, norm_weight, lm_head):
+    """llama.py:316-322."""
+    return torch.nn.functional.linear(rmsnorm(hidden, norm_weight, shape.rms_norm_eps), lm_head).float()

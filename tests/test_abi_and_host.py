@@ -148,3 +148,28 @@ def test_product_sequoia_utils_match_reference_fixtures():
         assert load_growmap("../umbrella/trees/" + name) == gm    # the path form of the reference's configs
     with pytest.raises(FileNotFoundError):
         load_growmap("no_such_tree.json")
+
+
+def test_engines_refuse_states_without_room_for_the_tree():
+    """the kernels write tree_size rows past num_nodes (505 for the shipped dynamic config), far more
+    than safe_buffer; validate_status / _prefill / _append must refuse such states on the host."""
+    from umbrella_b200.speculation.dynamic_speculation_engine import DynamicSpeculationEngine
+    from umbrella_b200.speculation.static_speculation_engine import StaticSpeculationEngine
+    dyn = object.__new__(DynamicSpeculationEngine)
+    dyn.max_length, dyn.safe_buffer, dyn.tree_size, dyn.tree_depth = 8192, 64, 505, 24
+    dyn.num_nodes = 8192 - 64                      # the reference's guard alone would let this through
+    assert not dyn.validate_status()
+    dyn.num_nodes = 8192 - 505 - 25
+    assert dyn.validate_status()
+    dyn.num_nodes += 1
+    assert not dyn.validate_status()
+    st = object.__new__(StaticSpeculationEngine)
+    st.max_length, st.safe_buffer, st.tree_size, st.tree_depth = 2048, 16, 43, 6      # safe_buffer < tree size
+    st.num_nodes = 2048 - 16
+    assert not st.validate_status()
+    st.num_nodes = 2048 - 43 - 7
+    assert st.validate_status()
+    import torch
+    assert st._prefill(torch.zeros(1, 2048 - 40, dtype=torch.int64)) is False       # refused before any tensor work
+    st.num_nodes = 1990
+    assert st._append(torch.zeros(1, 20, dtype=torch.int64)) is False

@@ -218,3 +218,33 @@ def test_stochastic_and_penalised_sampling_paths(engine_kind):
         hits = (topk_ids == new[:, None]).any(-1)
         assert hits.float().mean() > 0.9          # fp16 noise may reorder the 8th / 9th logit once in a while
     assert torch.equal(outs[0], outs[1])
+
+
+def test_append_after_lazily_skipped_leaf_row():
+    """with lazy_leaf_kv the draft K/V row of an accepted last-level node is written by the NEXT
+    build_tree; a multi-turn ``_append`` in between must re-derive it.  Same scripted run with both schedules,
+    an append after every few iterations: identical tokens, and the draft cache rows agree (fp16 noise)."""
+    from umbrella_b200.speculation.scripted import ScriptedAcceptance
+    g = torch.Generator().manual_seed(31)
+    prompt = torch.randint(3, TARGET.vocab_size, (1, 40), generator=g).to(DEV)
+    extra = [torch.randint(3, TARGET.vocab_size, (1, 7), generator=g).to(DEV) for _ in range(3)]
+    caches, toks = [], []
+    for lazy in (False, True):
+        eng = _engine(draft_same=True, graph=False, lazy=lazy)
+        # accept whole chains (rank-0 child always accepted): the last-level node is accepted every iteration
+        eng.acceptance_script = ScriptedAcceptance(eng.Successors, seed=3, max_iters=64, device=DEV, acc=[1.0, 0.0, 0.0, 0.0])
+        assert eng._prefill(prompt)
+        for turn in range(3):
+            for _ in range(4):
+                eng.build_tree()
+                eng.verify()
+            assert eng.last_accept_length == eng.tree_depth      # a leaf was accepted: its draft row is pending
+            assert eng._append(extra[turn])
+        n = eng.num_nodes
+        toks.append(eng.tokens[0, :n + 1].cpu())
+        caches.append((eng.draft_model.kv_cache.k_cache[:, :n].float().cpu(),
+                       eng.draft_model.kv_cache.v_cache[:, :n].float().cpu()))
+        assert eng.draft_model.kv_cache.kv_offset == n == eng.target_model.kv_cache.kv_offset
+    assert torch.equal(toks[0], toks[1])
+    for a, b in zip(caches[0], caches[1]):
+        assert torch.allclose(a, b, atol=4e-3, rtol=2e-2)

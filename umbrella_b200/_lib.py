@@ -72,7 +72,7 @@ SIGNATURES = {
                                   c_int64, C.POINTER(AttnMask), c_float, c_float, c_void_p, c_size_t, c_void_p]),
     "umb_rope_append_f16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
-    "umb_tree_accept": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+    "umb_tree_accept": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_int, c_void_p, c_void_p]),
     "umb_kv_gather": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p, c_int,
                               c_void_p]),
@@ -92,8 +92,8 @@ SIGNATURES = {
                                         c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "umb_llama_forward_dyn": (c_int, [C.POINTER(LlamaModel), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
-    "umb_store_tokens": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
-    "umb_dyn_tree_expand": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+    "umb_store_tokens": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "umb_dyn_tree_expand": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),
 }
 

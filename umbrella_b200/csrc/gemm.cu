@@ -599,6 +599,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         // slab does not queue behind ~85 KB of weights, starts the first MMA 2 us sooner but measured no faster:
         // the dequant warps set the pace.)
         const int n_early = n_pre;
+#ifdef UMB_EXP_XSKIP
+        int x_issue_count = 0;
+#endif
         int tile = tile0, g = in_tile0;                          // (tile, g) of the next weight copy
         auto issue_w = [&](int stage) {
             mbar_arrive_expect_tx(full_w + stage, kWTxBytes);
@@ -608,6 +611,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 tma_tensor2d_g2s(s_w + stage * kWStride, &tmap_w, g * 64, tile * kTileN, full_w + stage, pol_w);
         };
         auto issue_x = [&](int stage, int gk) {
+#ifdef UMB_EXP_XSKIP   // timing-only experiment (wrong numerics): fetch the x slab for one unit in UMB_EXP_XSKIP only
+            if ((x_issue_count++ % UMB_EXP_XSKIP) != 0) {
+                mbar_arrive(full_x + stage);
+                return;
+            }
+#endif
             mbar_arrive_expect_tx(full_x + stage, (uint32_t)kXBytes);
             unsigned char* xs = s_x + stage * kXBytes;
             if constexpr (kAwq) {

@@ -22,8 +22,9 @@ constexpr int kMaxTree = 1024;
 __global__ void __launch_bounds__(kAcceptThreads, 1)
 tree_accept_kernel(const int64_t* __restrict__ sampled, int64_t* __restrict__ tokens,
                    int64_t* __restrict__ position_ids, const int32_t* __restrict__ parents,
-                   const int32_t* __restrict__ depth, int N, int num_nodes_host, int32_t* __restrict__ state,
-                   const int64_t* __restrict__ eos, int n_eos, int32_t* __restrict__ result) {
+                   const int32_t* __restrict__ depth, int N, int num_nodes_host, int capacity,
+                   int32_t* __restrict__ state, const int64_t* __restrict__ eos, int n_eos,
+                   int32_t* __restrict__ result) {
     __shared__ unsigned char s_acc[kMaxTree];
     __shared__ int s_path[kMaxTree];
     __shared__ long long s_pos[kMaxTree];
@@ -33,7 +34,10 @@ tree_accept_kernel(const int64_t* __restrict__ sampled, int64_t* __restrict__ to
     pdl_launch_dependents();
     pdl_wait();
     const int i = threadIdx.x;
-    const int n = state ? state[0] : num_nodes_host;
+    int n = state ? state[0] : num_nodes_host;
+    // `capacity` = elements of tokens / position_ids: a prefix that leaves no room for the tree is a host-side
+    // bookkeeping error (the engines refuse such a state); never index past the buffers because of it
+    if (n + N > capacity) n = capacity - N > 0 ? capacity - N : 0;
     const int lane = i & 31, warp = i >> 5;
 
     long long spec = 0;
@@ -78,7 +82,7 @@ tree_accept_kernel(const int64_t* __restrict__ sampled, int64_t* __restrict__ to
     __syncthreads();
     if (i < len) tokens[n + i] = tok_j;
     if (i == len) tok_j = bonus;
-    if (i == len) tokens[n + len] = bonus;
+    if (i == len && n + len < capacity) tokens[n + len] = bonus;
     // EOS scan over tokens[n : n + len + 1]
     if (i <= len) {
         bool hit = false;
@@ -97,7 +101,7 @@ tree_accept_kernel(const int64_t* __restrict__ sampled, int64_t* __restrict__ to
     __syncthreads();
     if (i < alen) position_ids[n + i] = s_pos[i];
     __syncthreads();
-    if (i < N) position_ids[new_n + i] = (long long)new_n + depth[i];
+    if (i < N && new_n + i < capacity) position_ids[new_n + i] = (long long)new_n + depth[i];
 
     if (i == 0) {
         result[0] = alen;
@@ -149,13 +153,14 @@ kv_gather_kernel(unsigned char* __restrict__ k_cache, unsigned char* __restrict_
 }  // namespace umb
 
 extern "C" int umb_tree_accept(const int64_t* sampled, int64_t* tokens, int64_t* position_ids, const int32_t* parents,
-                               const int32_t* depth, int N, int num_nodes, int32_t* state, const int64_t* eos,
-                               int n_eos, int32_t* result, umb_stream_t stream) {
+                               const int32_t* depth, int N, int num_nodes, int capacity, int32_t* state,
+                               const int64_t* eos, int n_eos, int32_t* result, umb_stream_t stream) {
     UMB_CHECK_ARG(sampled && tokens && position_ids && parents && depth && result);
     UMB_CHECK_ARG(N >= 1 && num_nodes >= 0 && n_eos >= 0 && (n_eos == 0 || eos));
+    UMB_CHECK_ARG(capacity >= N && (state || num_nodes + N <= capacity));
     if (N >= umb::kMaxTree) return UMB_ERR_UNSUPPORTED;
     UMB_LAUNCH_PDL(umb::tree_accept_kernel, dim3(1), dim3(umb::kAcceptThreads), 0, (cudaStream_t)stream, sampled, tokens,
-                   position_ids, parents, depth, N, num_nodes, state, eos, n_eos, result);
+                   position_ids, parents, depth, N, num_nodes, capacity, state, eos, n_eos, result);
     umb::count_launches(1);
     return UMB_OK;
 }
@@ -176,19 +181,20 @@ extern "C" int umb_kv_gather(void* k_cache, void* v_cache, int num_planes, int64
 
 namespace umb {
 __global__ void store_tokens_kernel(int64_t* __restrict__ tokens, const int32_t* __restrict__ n_dev, int offset,
-                                    const int64_t* __restrict__ src, int count) {
+                                    const int64_t* __restrict__ src, int count, int capacity) {
     pdl_launch_dependents();
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) tokens[(int64_t)n_dev[0] + offset + i] = src[i];
+    const int64_t at = (int64_t)n_dev[0] + offset + i;
+    if (i < count && at < capacity) tokens[at] = src[i];
 }
 }  // namespace umb
 
 extern "C" int umb_store_tokens(int64_t* tokens_base, const int32_t* n_dev, int offset, const int64_t* src, int count,
-                                umb_stream_t stream) {
-    UMB_CHECK_ARG(tokens_base && n_dev && src && count >= 1 && offset >= 0);
+                                int capacity, umb_stream_t stream) {
+    UMB_CHECK_ARG(tokens_base && n_dev && src && count >= 1 && offset >= 0 && capacity >= 1);
     UMB_LAUNCH_PDL(umb::store_tokens_kernel, dim3((count + 127) / 128), dim3(128), 0, (cudaStream_t)stream, tokens_base,
-                   n_dev, offset, src, count);
+                   n_dev, offset, src, count, capacity);
     umb::count_launches(1);
     return UMB_OK;
 }
@@ -210,8 +216,8 @@ constexpr int kMaxCand = 4096;
 
 __global__ void __launch_bounds__(kExpandThreads, 1)
 dyn_tree_expand_kernel(const float* __restrict__ topk_logits, const int64_t* __restrict__ topk_ids, int rows, int beams,
-                       int width, int level_first, int num_nodes_host, const int32_t* __restrict__ n_dev,
-                       float* __restrict__ tree_score, int64_t* __restrict__ tokens, int32_t* __restrict__ parents,
+                       int width, int level_first, int num_nodes_host, int capacity,
+                       const int32_t* __restrict__ n_dev, float* __restrict__ tree_score, int64_t* __restrict__ tokens, int32_t* __restrict__ parents,
                        uint32_t* __restrict__ tree_bits, int tree_words) {
     __shared__ float s_cand[kMaxCand];
     __shared__ float s_row_max[128], s_row_sum[128];
@@ -254,7 +260,7 @@ dyn_tree_expand_kernel(const float* __restrict__ topk_logits, const int64_t* __r
             const int id = level_first + rows + rank;
             const int par = level_first + c / beams;
             tree_score[id] = v;
-            tokens[(int64_t)n + id] = topk_ids[c];
+            if (n + id < capacity) tokens[(int64_t)n + id] = topk_ids[c];
             parents[id] = par;
             for (int w = 0; w < tree_words; ++w) {
                 uint32_t bits = tree_bits[(int64_t)par * tree_words + w];
@@ -267,15 +273,16 @@ dyn_tree_expand_kernel(const float* __restrict__ topk_logits, const int64_t* __r
 }  // namespace umb
 
 extern "C" int umb_dyn_tree_expand(const float* topk_logits, const int64_t* topk_ids, int rows, int beams, int width,
-                                   int level_first, int num_nodes, const int32_t* n_dev, float* tree_score,
-                                   int64_t* tokens, int32_t* parents, uint32_t* tree_bits, int tree_words,
+                                   int level_first, int num_nodes, int capacity, const int32_t* n_dev,
+                                   float* tree_score, int64_t* tokens, int32_t* parents, uint32_t* tree_bits, int tree_words,
                                    umb_stream_t stream) {
     UMB_CHECK_ARG(topk_logits && topk_ids && tree_score && tokens && parents && tree_bits);
     UMB_CHECK_ARG(rows >= 1 && rows <= 128 && beams >= 1 && width >= 1 && level_first >= 0 && num_nodes >= 0);
+    UMB_CHECK_ARG(capacity >= 1 && (n_dev || num_nodes + level_first + rows + width <= capacity));
     UMB_CHECK_ARG(width <= rows * beams && tree_words >= 1 && (level_first + rows + width) <= tree_words * 32);
     if (rows * beams > umb::kMaxCand) return UMB_ERR_UNSUPPORTED;
     UMB_LAUNCH_PDL(umb::dyn_tree_expand_kernel, dim3(1), dim3(umb::kExpandThreads), 0, (cudaStream_t)stream, topk_logits,
-                   topk_ids, rows, beams, width, level_first, num_nodes, n_dev, tree_score, tokens, parents, tree_bits,
+                   topk_ids, rows, beams, width, level_first, num_nodes, capacity, n_dev, tree_score, tokens, parents, tree_bits,
                    tree_words);
     umb::count_launches(1);
     return UMB_OK;

@@ -224,14 +224,15 @@ def tree_accept(sampled, tokens, position_ids, parents, depth, num_nodes: int, e
     _cuda(depth, torch.int32, "depth"), _cuda(result, torch.int32, "result")
     assert result.numel() >= 4 + N
     check(_lib.load().umb_tree_accept(_p(sampled), _p(tokens), _p(position_ids), _p(parents), _p(depth), N, num_nodes,
-                                      _p(state), _p(eos), 0 if eos is None else eos.numel(), _p(result), _stream()),
+                                      min(tokens.numel(), position_ids.numel()), _p(state), _p(eos), 0 if eos is None else eos.numel(), _p(result), _stream()),
           "tree_accept")
 
 
 def store_tokens(tokens: torch.Tensor, n_dev: torch.Tensor, offset: int, src: torch.Tensor):
     """tokens[n_dev[0] + offset + i] = src[i] with n read on the device (graph replay)."""
     _cuda(tokens, torch.int64, "tokens"), _cuda(src, torch.int64, "src"), _cuda(n_dev, torch.int32, "n_dev")
-    check(_lib.load().umb_store_tokens(_p(tokens), _p(n_dev), offset, _p(src), src.numel(), _stream()), "store_tokens")
+    check(_lib.load().umb_store_tokens(_p(tokens), _p(n_dev), offset, _p(src), src.numel(), tokens.numel(), _stream()),
+          "store_tokens")
 
 
 def dyn_tree_expand(topk_logits: torch.Tensor, topk_ids: torch.Tensor, width: int, level_first: int, num_nodes: int,
@@ -246,7 +247,7 @@ def dyn_tree_expand(topk_logits: torch.Tensor, topk_ids: torch.Tensor, width: in
     assert topk_logits.is_contiguous() and topk_ids.is_contiguous() and topk_logits.shape == topk_ids.shape
     rows, beams = topk_logits.shape
     check(_lib.load().umb_dyn_tree_expand(_p(topk_logits), _p(topk_ids), rows, beams, width, level_first, num_nodes,
-                                          _p(n_dev), _p(tree_score), _p(tokens), _p(parents), _p(tree_bits),
+                                          tokens.numel(), _p(n_dev), _p(tree_score), _p(tokens), _p(parents), _p(tree_bits),
                                           tree_bits.shape[1], _stream()), "dyn_tree_expand")
 
 

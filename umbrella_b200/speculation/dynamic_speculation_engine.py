@@ -96,6 +96,12 @@ class DynamicSpeculationEngine(BaseEngine):
         self.eos_tokens = list(eos_tokens)
         self._eos_dev = torch.tensor(self.eos_tokens, dtype=torch.int64, device=self.device) if self.eos_tokens else None
 
+    def _has_room(self, num_nodes: int) -> bool:
+        """width * depth + 1 tree rows (385 / 505 in the shipped configs) are written past num_nodes into tokens,
+        position_ids and both KV caches -- far more than safe_buffer (64), which is all the reference guards with
+        (dynamic...:103, 329); a state without room for the tree is refused instead of reaching the kernels."""
+        return num_nodes + self.tree_size + self.tree_depth + 1 <= self.max_length
+
     # ------------------------------------------------------------------ prefill / append (dynamic...:90-166)
     def _encode(self, text):
         if self.tokenizer is None:
@@ -117,7 +123,7 @@ class DynamicSpeculationEngine(BaseEngine):
     @torch.inference_mode()
     def _prefill(self, input_ids: torch.LongTensor):
         prefix_len = input_ids.shape[1]
-        if prefix_len >= self.max_length - 2 * self.safe_buffer:
+        if prefix_len >= self.max_length - 2 * self.safe_buffer or not self._has_room(self.num_nodes + prefix_len):
             return False
         self.num_nodes += prefix_len
         self.num_nodes_this_iter = self.num_nodes + self.tree_size
@@ -133,7 +139,8 @@ class DynamicSpeculationEngine(BaseEngine):
     @torch.inference_mode()
     def _append(self, input_ids: torch.LongTensor):
         append_len = input_ids.shape[1]
-        if append_len + self.num_nodes >= self.max_length - 2 * self.safe_buffer:
+        if append_len + self.num_nodes >= self.max_length - 2 * self.safe_buffer \
+                or not self._has_room(self.num_nodes + append_len + 1):
             return False
         self.tokens[:, self.num_nodes + 1:self.num_nodes + 1 + append_len].copy_(input_ids)
         last = self.num_nodes
@@ -225,7 +232,7 @@ class DynamicSpeculationEngine(BaseEngine):
         self.target_model.clear()
 
     def validate_status(self):
-        return self.num_nodes <= (self.max_length - self.safe_buffer)
+        return self.num_nodes <= (self.max_length - self.safe_buffer) and self._has_room(self.num_nodes)
 
     def update_generation_args(self, **generation_args):
         self.temperature = generation_args.pop("temperature", self.temperature)

@@ -138,6 +138,13 @@ class StaticSpeculationEngine(BaseEngine):
         self._state[:3] = torch.tensor([self.num_nodes, self.num_nodes + self.tree_size, self.num_nodes],
                                        dtype=torch.int32)
 
+    def _has_room(self, num_nodes: int) -> bool:
+        """The kernels index tokens / position_ids / both KV caches at rows up to num_nodes + tree_size (tree rows,
+        the next tree's positions, the bonus token).  The reference only guards with safe_buffer and fails with a
+        shape error beyond it (static...:146-147, 351); here a state without room is refused (``False``), so a
+        growmap larger than safe_buffer or a long multi-turn prefix can never reach a device-side write."""
+        return num_nodes + self.tree_size + self.tree_depth + 1 <= self.max_length
+
     # ------------------------------------------------------------------ prefill / append (static...:133-209)
     def _encode(self, text):
         if self.tokenizer is None:
@@ -153,7 +160,7 @@ class StaticSpeculationEngine(BaseEngine):
     @torch.inference_mode()
     def _prefill(self, input_ids: torch.LongTensor):
         prefix_len = input_ids.shape[1]
-        if prefix_len >= self.max_length - 2 * self.safe_buffer:
+        if prefix_len >= self.max_length - 2 * self.safe_buffer or not self._has_room(self.num_nodes + prefix_len):
             return False
         self.num_nodes += prefix_len
         self.num_nodes_this_iter = self.num_nodes + self.tree_size
@@ -171,7 +178,8 @@ class StaticSpeculationEngine(BaseEngine):
     @torch.inference_mode()
     def _append(self, input_ids: torch.LongTensor):
         append_len = input_ids.shape[1]
-        if append_len + self.num_nodes >= self.max_length - 2 * self.safe_buffer:
+        if append_len + self.num_nodes >= self.max_length - 2 * self.safe_buffer \
+                or not self._has_room(self.num_nodes + append_len + 1):
             return False
         self.tokens[:, self.num_nodes + 1:self.num_nodes + 1 + append_len].copy_(input_ids)
         last = self.num_nodes
@@ -181,7 +189,15 @@ class StaticSpeculationEngine(BaseEngine):
         self.position_ids[:, :self.num_nodes] = torch.arange(self.num_nodes, device=self.device).unsqueeze(0)
         self.position_ids[:, self.num_nodes:self.num_nodes + self.tree_size] = self.num_nodes + self.depth64
         ids, pos = self.tokens[0, last:self.num_nodes], self.position_ids[0, last:self.num_nodes]
-        self.draft_model.prefill_forward(ids, pos, want_logits=False)
+        if bool(self.lazy_leaf_kv) and self.tree_depth >= 2 and last >= 1:
+            # lazy_leaf_kv leaves the draft K/V row of an accepted last-level node (row last - 1) unwritten and
+            # relies on the NEXT build_tree recomputing it; an append comes in between, so the draft prefill starts
+            # one row earlier and re-derives that row together with the appended ones
+            self.draft_model.kv_cache.kv_offset = last - 1
+            self.draft_model.prefill_forward(self.tokens[0, last - 1:self.num_nodes],
+                                             self.position_ids[0, last - 1:self.num_nodes], want_logits=False)
+        else:
+            self.draft_model.prefill_forward(ids, pos, want_logits=False)
         logits = self.target_model.prefill_forward(ids, pos, last_only=True)
         self.tokens[0, self.num_nodes] = ops.argmax(logits)[0]
         self._sync_state()
@@ -226,7 +242,7 @@ class StaticSpeculationEngine(BaseEngine):
         n, N = self.num_nodes, self.tree_size
         bucket = self.graph_bucket
         bound = min(self.max_length, ((n + N) // bucket + 1) * bucket)
-        key = (bound, id(self.acceptance_script))
+        key = (bound, id(self.acceptance_script), bool(self._lazy()))
         g = self._graphs.get(key)
         if g is None:
             # first iteration of this bucket runs eagerly (it is also the warm-up), then the graph is captured
@@ -345,7 +361,7 @@ class StaticSpeculationEngine(BaseEngine):
         self._state.zero_()
 
     def validate_status(self):
-        return self.num_nodes <= (self.max_length - self.safe_buffer)
+        return self.num_nodes <= (self.max_length - self.safe_buffer) and self._has_room(self.num_nodes)
 
     def update_generation_args(self, **generation_args):
         self.temperature = generation_args.pop("temperature", self.temperature)
