@@ -215,6 +215,26 @@ int umb_add_f16(const void* a, const void* b, void* y, int64_t n, umb_stream_t s
 int umb_embedding_f16(const int64_t* ids, const void* table, void* y, int rows, int hidden, umb_stream_t stream);
 /* first-occurrence arg-max over each row of fp32 logits [rows, vocab] -> int64[rows] */
 int umb_argmax_f32(const float* logits, int64_t ld, int rows, int vocab, int64_t* out, umb_stream_t stream);
+/* Fused target-side sampling of verify() over fp32 logits [rows, vocab] (one token per tree node):
+ * repetition penalty -> top-k -> softmax(T) -> top-p -> draw, or the arg-max of the penalised logits.
+ *   UMB_SAMPLE_STATIC   static_speculation_engine.py:305-310: flashinfer top_k_top_p_sampling_from_logits(
+ *                       logits / T, uniform_samples[rounds, rows], top_k, top_p) -- top-k mask, softmax, then
+ *                       top-p rejection rounds driven by the caller's FIXED uniforms (deterministic)
+ *   UMB_SAMPLE_DYNAMIC  dynamic_speculation_engine.py:276-281: apply_topk, softmax(logits / T), top_p_renorm_prob,
+ *                       then the inverse CDF (ascending token id) at uniforms[row] in place of torch.multinomial
+ *   UMB_SAMPLE_ARGMAX   T < 0.05 with repetition_penalty > 1.01 (static...:298-307): first-occurrence arg-max
+ * penalty_ids: the token ids seen so far (speculation_utils.py:340-345; shared by all rows), count =
+ * penalty_count (+ penalty_count_dev[0] when that device pointer is given); ignored unless penalty > 1.01.
+ * top_k <= 1024.  out int64[rows]. */
+enum {
+    UMB_SAMPLE_STATIC = 0,
+    UMB_SAMPLE_DYNAMIC = 1,
+    UMB_SAMPLE_ARGMAX = 2
+};
+int umb_sample_f32(const float* logits, int64_t ld, int rows, int vocab, int mode, float temperature, int top_k,
+                   float top_p, const float* uniforms, int rounds, const int64_t* penalty_ids, int penalty_count,
+                   const int32_t* penalty_count_dev, float penalty, int64_t* out, umb_stream_t stream);
+
 /* decode the UMB_EPI_LOGITS arg-max keys into int64 token ids */
 int umb_argmax_keys_to_ids(const unsigned long long* keys, int rows, int64_t* out, umb_stream_t stream);
 

@@ -8,5 +8,5 @@ for v in "" xskip4 xskip1000; do
 done > gpurun_out/r2_xskip.txt 2>&1
 cat gpurun_out/r2_xskip.txt
 unset UMB_LIB_PATH
-timeout 900 python -m pytest tests/test_gpu_engine.py tests/test_gpu_tree.py tests/test_gpu_dynamic.py -m gpu -x -q > gpurun_out/r2_pytest2.txt 2>&1
-echo "pytest rc=$?"; tail -5 gpurun_out/r2_pytest2.txt
+timeout 900 python -m pytest tests/test_gpu_sampling.py tests/test_gpu_engine.py tests/test_gpu_tree.py tests/test_gpu_dynamic.py -m gpu -q -s > gpurun_out/r2_pytest2.txt 2>&1
+echo "pytest rc=$?"; grep -E "TV distance|passed|failed|Error|assert" gpurun_out/r2_pytest2.txt | tail -30

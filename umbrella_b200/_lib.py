@@ -17,6 +17,7 @@ c_void_p, c_int, c_int64, c_size_t, c_float = C.c_void_p, C.c_int, C.c_int64, C.
 
 UMB_EPI_STORE, UMB_EPI_RESIDUAL, UMB_EPI_SILU_MUL, UMB_EPI_LOGITS, UMB_EPI_ROPE_QKV = 0, 1, 2, 3, 4
 UMB_MASK_TREE, UMB_MASK_DENSE, UMB_MASK_CAUSAL = 0, 1, 2
+UMB_SAMPLE_STATIC, UMB_SAMPLE_DYNAMIC, UMB_SAMPLE_ARGMAX = 0, 1, 2
 
 
 class Epilogue(C.Structure):
@@ -92,6 +93,8 @@ SIGNATURES = {
                                         c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "umb_llama_forward_dyn": (c_int, [C.POINTER(LlamaModel), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "umb_sample_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_int, c_void_p,
+                               c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "umb_store_tokens": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "umb_dyn_tree_expand": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libumbrella_b200.so")
-SOURCES = ["api.cu", "tree.cu", "glue.cu", "attn.cu", "gemm.cu", "forward.cu"]
+SOURCES = ["api.cu", "tree.cu", "glue.cu", "attn.cu", "gemm.cu", "forward.cu", "sampler.cu"]
 HEADERS = ["common.cuh", "internal.h", os.path.join("..", "..", "include", "umbrella_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

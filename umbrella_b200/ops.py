@@ -11,9 +11,11 @@ import torch
 
 from . import _lib
 from ._lib import (AttnMask, Epilogue, RopeEpilogue, UMB_EPI_LOGITS, UMB_EPI_RESIDUAL, UMB_EPI_ROPE_QKV, UMB_EPI_SILU_MUL,
-                   UMB_EPI_STORE, UMB_MASK_CAUSAL, UMB_MASK_DENSE, UMB_MASK_TREE, check)
+                   UMB_EPI_STORE, UMB_MASK_CAUSAL, UMB_MASK_DENSE, UMB_MASK_TREE, UMB_SAMPLE_ARGMAX, UMB_SAMPLE_DYNAMIC,
+                   UMB_SAMPLE_STATIC, check)
 
 GROUP = 128
+SAMPLE_MAX_TOPK = 1024      # umb_sample_f32 keeps the top-k survivors of a row in shared memory
 
 
 def _p(t: torch.Tensor | None):
@@ -300,6 +302,35 @@ def argmax(logits: torch.Tensor) -> torch.Tensor:
     rows, vocab = logits.shape
     out = torch.empty(rows, dtype=torch.int64, device=logits.device)
     check(_lib.load().umb_argmax_f32(_p(logits), logits.stride(0), rows, vocab, _p(out), _stream()), "argmax")
+    return out
+
+
+def sample(logits: torch.Tensor, mode: int, *, temperature: float = 1.0, top_k: int = 32, top_p: float = 0.9,
+           uniforms: torch.Tensor | None = None, penalty_ids: torch.Tensor | None = None, penalty: float = 1.0,
+           penalty_count: int | None = None, penalty_count_dev: torch.Tensor | None = None,
+           out: torch.Tensor | None = None) -> torch.Tensor:
+    """Fused target sampling (umb_sample_f32): repetition penalty -> top-k -> softmax(T) -> top-p -> one token per
+    row.  ``uniforms``: fp32 [rounds, rows] (UMB_SAMPLE_STATIC, the engine's fixed uniform_samples) or [rows]
+    (UMB_SAMPLE_DYNAMIC).  ``penalty_ids``: int64 ids seen so far (first ``penalty_count`` entries, plus
+    ``penalty_count_dev[0]`` when given)."""
+    _cuda(logits, torch.float32, "logits")
+    assert logits.dim() == 2 and logits.stride(1) == 1
+    rows, vocab = logits.shape
+    if out is None:
+        out = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    rounds = 0
+    if mode != UMB_SAMPLE_ARGMAX:
+        _cuda(uniforms, torch.float32, "uniforms")
+        assert uniforms.is_contiguous() and uniforms.shape[-1] == rows
+        rounds = uniforms.shape[0] if uniforms.dim() == 2 else 1
+    count = 0
+    if penalty_ids is not None:
+        _cuda(penalty_ids, torch.int64, "penalty_ids")
+        assert penalty_ids.is_contiguous()
+        count = penalty_ids.numel() if penalty_count is None else penalty_count
+    check(_lib.load().umb_sample_f32(_p(logits), logits.stride(0), rows, vocab, mode, float(temperature), int(top_k),
+                                     float(top_p), _p(uniforms), rounds, _p(penalty_ids), count, _p(penalty_count_dev),
+                                     float(penalty), _p(out), _stream()), "sample")
     return out
 
 

@@ -24,7 +24,7 @@ import torch
 from .. import ops
 from ..models.auto_model import AutoModelLM
 from .base import BaseEngine
-from .speculation_utils import apply_repetition_penalty, apply_topk, is_sentence_complete_regex
+from .speculation_utils import is_sentence_complete_regex, sample_topk_topp_torch
 
 
 class DynamicSpeculationEngine(BaseEngine):
@@ -174,24 +174,24 @@ class DynamicSpeculationEngine(BaseEngine):
                                     self.parents, self.tree_bits)
 
     def _sample_target(self, logits: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
-        """dynamic...:265-281.  Greedy: decode the arg-max keys produced by the lm_head epilogue."""
+        """dynamic...:265-281.  Greedy: decode the arg-max keys produced by the lm_head epilogue.  Otherwise ONE fused
+        kernel (umb_sample_f32): repetition penalty, apply_topk, softmax(T), top_p_renorm_prob's nucleus and the draw.
+        The reference draws with torch.multinomial; here one uniform per node from torch's generator (so
+        torch.manual_seed reproduces a run) goes through the inverse CDF -- the same distribution."""
         n, N = self.num_nodes, self.tree_size
         penalised = self.repetition_penalty > 1.01
-        if penalised:
-            logits = apply_repetition_penalty(self.tokens[:, :n + 1].expand(N, -1), logits, self.repetition_penalty)
-        if self.temperature < 0.05:
-            ids = ops.argmax_keys_to_ids(keys)        # also resets the keys for the next forward
-            return ops.argmax(logits.contiguous()) if penalised else ids
+        if self.temperature < 0.05 and not penalised:
+            return ops.argmax_keys_to_ids(keys)       # also resets the keys for the next forward
         ops.argmax_keys_to_ids(keys)
-        logits = apply_topk(logits, topk=self.topk)
-        proba = torch.softmax(logits / self.temperature, dim=-1)
-        # flashinfer.sampling.top_p_renorm_prob (dynamic...:280): keep the smallest top set whose mass reaches
-        # topp, renormalise
-        sp, si = proba.sort(dim=-1, descending=True)
-        keep = (sp.cumsum(-1) - sp) < self.topp
-        sp = sp * keep
-        pick = torch.multinomial(sp / sp.sum(-1, keepdim=True), 1)
-        return si.gather(-1, pick).squeeze(-1)
+        pen = dict(penalty_ids=self.tokens[0], penalty_count=n + 1, penalty=self.repetition_penalty) if penalised else {}
+        if self.temperature < 0.05:
+            return ops.sample(logits, ops.UMB_SAMPLE_ARGMAX, **pen)
+        self.last_uniforms = torch.rand(N, device=logits.device)
+        if self.topk > ops.SAMPLE_MAX_TOPK:
+            return sample_topk_topp_torch(logits, self.temperature, self.topk, self.topp, self.last_uniforms,
+                                          static=False, **pen)
+        return ops.sample(logits, ops.UMB_SAMPLE_DYNAMIC, temperature=self.temperature, top_k=self.topk, top_p=self.topp,
+                          uniforms=self.last_uniforms, **pen)
 
     @torch.inference_mode()
     def verify(self):

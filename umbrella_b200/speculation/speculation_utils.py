@@ -43,3 +43,44 @@ def apply_topk(logits: torch.FloatTensor, topk: int):
 def is_sentence_complete_regex(text):
     """speculation_utils.py:356-358."""
     return bool(re.search(r'[.?!。？！]\s*$', text))
+
+
+def sample_topk_topp_torch(logits: torch.Tensor, temperature: float, topk: int, topp: float, uniforms: torch.Tensor,
+                           static: bool, penalty_ids: torch.Tensor | None = None, penalty_count: int = 0,
+                           penalty: float = 1.0) -> torch.Tensor:
+    """The sampling of umb_sample_f32 as torch device ops, for top-k values beyond the kernel's shared-memory
+    survivor list (topk > 1024; the shipped configs use 32).  Same algorithm: penalty -> top-k (ties at the k-th
+    value stay) -> softmax(T) -> nucleus {j: mass(p > p_j) < topp}; ``static``: flashinfer's rejection rounds with
+    the fixed uniforms [R, N] (static...:310), else the inverse CDF at uniforms [N] (dynamic...:278-281)."""
+    if penalty_ids is not None and penalty > 1.01:
+        ids = penalty_ids[:penalty_count].unsqueeze(0).expand(logits.shape[0], -1)
+        logits = apply_repetition_penalty(ids, logits, penalty)
+    x = logits / temperature if static else logits
+    kth = torch.topk(x, min(topk, x.size(-1)))[0][..., -1, None]
+    x = x.masked_fill(x < kth, -torch.inf)
+    p = torch.softmax(x if static else x / temperature, dim=-1)
+    rows = torch.arange(p.shape[0], device=p.device)
+    if not static:
+        sp = p.sort(dim=-1, descending=True).values
+        before = sp.cumsum(-1) - sp                                     # mass strictly ahead in sorted order
+        first = torch.ones_like(sp, dtype=torch.bool)
+        first[:, 1:] = sp[:, 1:] != sp[:, :-1]
+        gt = torch.where(first, before, torch.zeros_like(before)).cummax(-1).values     # ties share their first's mass
+        vmin = torch.where(gt < topp, sp, torch.full_like(sp, torch.inf)).min(-1, keepdim=True).values
+        kept = torch.where(p >= vmin, p, torch.zeros_like(p))
+        cdf = kept.cumsum(-1)
+        u = uniforms.reshape(-1, 1) * cdf[:, -1:]
+        return (cdf > u).int().argmax(-1)
+    q = torch.ones(p.shape[0], 1, device=p.device)
+    pivot = torch.zeros_like(q)
+    done = torch.zeros(p.shape[0], dtype=torch.bool, device=p.device)
+    out = torch.zeros(p.shape[0], dtype=torch.int64, device=p.device)
+    for r in range(uniforms.shape[0]):
+        live = torch.where(p > pivot, p, torch.zeros_like(p))
+        cdf = live.cumsum(-1)
+        s = (cdf > uniforms[r].reshape(-1, 1) * q).int().argmax(-1)
+        out = torch.where(done, out, s)
+        pivot = torch.where(done[:, None], pivot, torch.maximum(pivot, p[rows, s][:, None]))
+        q = torch.where(p > pivot, p, torch.zeros_like(p)).sum(-1, keepdim=True)
+        done = done | (q[:, 0] < topp)
+    return out

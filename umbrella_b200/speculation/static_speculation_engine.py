@@ -22,7 +22,7 @@ from .. import _lib, ops
 from ..models.auto_model import AutoModelLM
 from ..sequoia_utils import load_growmap, tree_bits_from_mask
 from .base import BaseEngine
-from .speculation_utils import apply_repetition_penalty, apply_topk, is_sentence_complete_regex
+from .speculation_utils import is_sentence_complete_regex, sample_topk_topp_torch
 
 
 class StaticSpeculationEngine(BaseEngine):
@@ -303,23 +303,23 @@ class StaticSpeculationEngine(BaseEngine):
             self.num_draft_tokens_this_iter = n + self.tree_size
 
     def _sample_target(self, logits: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
-        """static...:298-310.  Greedy: decode the arg-max keys produced by the lm_head epilogue."""
-        n, N = self.num_nodes, self.tree_size
-        if self.repetition_penalty > 1.01:
-            logits = apply_repetition_penalty(self.tokens[:, :n + 1].expand(N, -1), logits, self.repetition_penalty)
-            ops.argmax_keys_to_ids(keys)              # drop (and reset) the un-penalised keys
-            if self.temperature < 0.05:
-                return ops.argmax(logits.contiguous())
-        if self.temperature < 0.05:
+        """static...:298-310.  Greedy: decode the arg-max keys produced by the lm_head epilogue.  Otherwise ONE fused
+        kernel (umb_sample_f32): repetition penalty over tokens[:n + 1], top-k, softmax(T), and the top-p rejection
+        rounds of flashinfer's top_k_top_p_sampling_from_logits driven by the fixed ``uniform_samples`` [3, N] drawn
+        at initialize() (static...:131) -- like the reference, a deterministic function of the logits."""
+        n = self.num_nodes
+        penalised = self.repetition_penalty > 1.01
+        if self.temperature < 0.05 and not penalised:
             return ops.argmax_keys_to_ids(keys)
-        ops.argmax_keys_to_ids(keys)
-        # stochastic: top-k -> softmax(T) -> top-p renormalisation -> one sample per node
-        probs = torch.softmax(apply_topk(logits, self.topk) / self.temperature, dim=-1)
-        sp, si = probs.sort(dim=-1, descending=True)
-        keep = (sp.cumsum(-1) - sp) < self.topp
-        sp = sp * keep
-        pick = torch.multinomial(sp / sp.sum(-1, keepdim=True), 1)
-        return si.gather(-1, pick).squeeze(-1)
+        ops.argmax_keys_to_ids(keys)                  # drop (and reset) the un-penalised keys
+        pen = dict(penalty_ids=self.tokens[0], penalty_count=n + 1, penalty=self.repetition_penalty) if penalised else {}
+        if self.temperature < 0.05:
+            return ops.sample(logits, ops.UMB_SAMPLE_ARGMAX, **pen)
+        if self.topk > ops.SAMPLE_MAX_TOPK:
+            return sample_topk_topp_torch(logits, self.temperature, self.topk, self.topp, self.uniform_samples,
+                                          static=True, **pen)
+        return ops.sample(logits, ops.UMB_SAMPLE_STATIC, temperature=self.temperature, top_k=self.topk, top_p=self.topp,
+                          uniforms=self.uniform_samples, **pen)
 
     @torch.inference_mode()
     def verify(self):
