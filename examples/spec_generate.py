@@ -21,6 +21,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default=None, help="a reference configs/*.json; default: the 70B-AWQ + 1B static config")
 ap.add_argument("--max-new-tokens", type=int, default=128)
 ap.add_argument("--prompt-len", type=int, default=256)
+ap.add_argument("--real-weights", action="store_true", help="load the safetensors checkpoints (local dir / HF cache) "
+                "instead of seeded synthetic weights of the same architectures")
 args = ap.parse_args()
 
 config = {"model": "hugging-quants/Meta-Llama-3.1-70B-Instruct-AWQ-INT4", "draft_model": "meta-llama/Llama-3.2-1B-Instruct",
@@ -30,6 +32,8 @@ if args.config:
     if "growmap_path" in config:
         config["growmap_path"] = os.path.basename(config["growmap_path"])      # shipped trees are looked up by name
 
+if not args.real_weights:
+    config["synthetic"] = True                                                # opt-in: no checkpoints offline
 engine = AutoEngine.from_config(device="cuda:0", **config)
 engine.initialize()
 engine._set_eos([])                                                           # random weights: do not stop on a stray EOS

@@ -5,36 +5,65 @@ TEST / MEASUREMENT INFRASTRUCTURE ONLY -- see oracle/__init__.py.  Used by ``ben
 
 What is timed: one decoder layer of the Llama-3.1-70B-AWQ verify forward over the N tree tokens, as
 a CPU implementation of the reference's path has to do it (reference call sites:
-umbrella/models/llama.py:262-303, umbrella/quantization/awq_utils.py:63-86): for each of the seven
-linears, unpack the INT4 checkpoint words, dequantise ``(q - z) * s`` to fp16 and multiply (the
-weights stay INT4 in memory: 37.7 GB for the model, an fp32 copy would be 274 GB), plus RMSNorm,
-RoPE, masked GQA attention over the prefix and SiLU.  The reference itself has no CPU path (it is
-GPU compute with optional host-RAM weight paging); this port is the closest CPU
-statement of the same arithmetic.  A full verify is 80 such layers + the fp16 lm_head; the sample
-is ONE layer (+ a 1/80 share of the lm_head), scaled by 80 and stated as such.
+umbrella/models/llama.py:262-303, umbrella/quantization/awq_utils.py:63-86).  The seven INT4 linears --
+99.9 % of the arithmetic -- run in the C restatement oracle/awq_cpu.c (weights stay INT4 in memory, one pass
+over them with unit stride, a 16-entry fp16((q - z) * s) table per column and group, pthreads over column
+blocks; no dequantised matrix is materialised); RMSNorm, RoPE, masked GQA attention over the prefix and SiLU
+are torch CPU ops.  The reference itself has no CPU path (it is GPU compute with optional host-RAM weight
+paging); this port is the closest CPU statement of the same arithmetic.  A full verify is 80
+such layers + the fp16 lm_head; the sample is ONE layer (+ a 1/80 share of the lm_head), scaled by 80 and
+stated as such.
 """
 from __future__ import annotations
 
 import math
 import time
 
-import numpy as np
 import torch
+
+import ctypes as C
+import os
+import subprocess
 
 from . import llama as ollama
 
-_NIB = np.array([0, 4, 1, 5, 2, 6, 3, 7])
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libawq_cpu.so")
+_lib = None
+_THREADS = [1]
 
 
-def _dequant_matmul(x16: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor,
-                    group: int) -> torch.Tensor:
-    """fp16(x @ fp16((q - z) * s)) with torch CPU kernels (all host threads)."""
-    shifts = torch.tensor(4 * _NIB, dtype=torch.int32)
-    q = ((qweight.unsqueeze(-1) >> shifts) & 0xF).reshape(qweight.shape[0], -1)            # [K, N]
-    z = ((qzeros.unsqueeze(-1) >> shifts) & 0xF).reshape(qzeros.shape[0], -1)              # [K/g, N]
-    w = ((q - z.repeat_interleave(group, dim=0)).to(torch.float32) * scales.float().repeat_interleave(group, dim=0))
-    w = w.to(torch.float16).float()
-    return (x16.float() @ w).to(torch.float16)
+def build_c_oracle(force: bool = False) -> str:
+    """make -C oracle (gcc, x86-64-v3, pthreads) -> oracle/_build/libawq_cpu.so."""
+    src = os.path.join(HERE, "awq_cpu.c")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return LIB
+
+
+def c_oracle():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build_c_oracle())
+    return _lib
+
+
+def awq_gemm_c(x16: torch.Tensor, qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, group: int,
+               threads: int | None = None) -> torch.Tensor:
+    """fp16(x @ fp16((q - z) * s)) through oracle/awq_cpu.c.  x16 [M, K] fp16 (any M)."""
+    x16 = x16.contiguous()
+    m, k = x16.shape
+    n = scales.shape[1]
+    y = torch.empty((m, n), dtype=torch.float32)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = c_oracle().oracle_awq_gemm(p(x16), p(qweight.contiguous()), p(qzeros.contiguous()), p(scales.contiguous()), m, k, n,
+                                    group, p(y), threads or _THREADS[0])
+    assert rc == 0, rc
+    return y.to(torch.float16)
+
+
+def _dequant_matmul(x16, qweight, qzeros, scales, group):
+    return awq_gemm_c(x16, qweight, qzeros, scales, group)
 
 
 class CpuLayerBaseline:
@@ -42,7 +71,9 @@ class CpuLayerBaseline:
                  seed: int = 1234, threads: int | None = None):
         if threads:
             torch.set_num_threads(threads)
-        self.threads = torch.get_num_threads()
+        self.threads = threads or os.cpu_count() or torch.get_num_threads()
+        _THREADS[0] = self.threads
+        c_oracle()
         self.shape, self.N, self.prefix = shape, tree_size, prefix
         self.w = ollama.synth_layer(shape, 0, awq=True, seed=seed)
         g = torch.Generator().manual_seed(seed)

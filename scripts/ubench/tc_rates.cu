@@ -144,6 +144,92 @@ __global__ void __launch_bounds__(512, 1) tmem_rw(long long* cyc, unsigned* sink
     }
 }
 
+
+// (3) contention: 2 MMA warps issue units (A from TMEM columns 256.., B from smem, `nacc` accumulators each) while
+//     `st_warps` other warps keep storing 32 KB "A operands" into tensor memory (tcgen05.st x16 x4 + wait::st per warp
+//     iteration = 8 KB per warp) and / or `ld_warps` warps keep loading accumulators.
+__global__ void __launch_bounds__(640, 1) mma_vs_st(long long* cyc, int nacc, int st_warps, int ld_warps, int units, int st_gap) {
+    __shared__ __align__(1024) unsigned char s_b[64 * 128];
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ volatile int s_stop;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64 * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_b)[i] = 0x3c003c00u;
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        fence_barrier_init();
+        s_stop = 0;
+    }
+    if (warp == 0) {
+        tmem_alloc(&s_tmem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    constexpr uint32_t idesc = umma_idesc_f16(128, 16);
+    const uint64_t bd0 = umma_smem_desc_sw128(smem_u32(s_b));
+    if (warp < 2) {
+        const uint32_t d_base = tmem + warp * (nacc * 16);
+        long long t0 = clock64();
+        for (int u = 0; u < units; ++u) {
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_ts_f16(d_base + (kk % nacc) * 16, tmem + 128 + 64 * (u % 6) + kk * 8, bd0 + (kk & 3) * 2, idesc,
+                                kk < nacc ? 0u : 1u);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(bar + warp);
+        __syncwarp();
+        mbar_wait(bar + warp, 0);
+        long long t1 = clock64();
+        if (lane == 0 && blockIdx.x == 0) cyc[warp] = t1 - t0;
+        if (lane == 0) atomicAdd((int*)&s_stop, 1);
+    } else if (warp < 2 + st_warps) {
+        const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128;
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = threadIdx.x + i;
+        long long n = 0, t0 = clock64();
+        while (s_stop < 2) {
+            const uint32_t col = base + 64 * (uint32_t)(n % 6);
+            UMB_TMEM_ST_X16(col, r);
+            UMB_TMEM_ST_X16(col + 16, r);
+            UMB_TMEM_ST_X16(col + 32, r);
+            UMB_TMEM_ST_X16(col + 48, r);
+            tc_wait_st();
+            ++n;
+            for (int g = 0; g < st_gap; ++g) __nanosleep(20);
+        }
+        long long t1 = clock64();
+        if (lane == 0 && blockIdx.x == 0 && warp == 2) {
+            cyc[2] = n;
+            cyc[3] = t1 - t0;
+        }
+    } else if (warp < 2 + st_warps + ld_warps) {
+        const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t r[16];
+        unsigned acc = 0;
+        while (s_stop < 2) {
+            UMB_TMEM_LD_X16(base, r);
+            tc_wait_ld();
+            acc += r[0];
+        }
+        if (acc == 0x12345678u) cyc[7] = acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 int main() {
     long long* cyc;
     unsigned* sink;
@@ -186,5 +272,26 @@ int main() {
             printf("  %-32s warps=%2d: %7.1f cyc/iter %s\n", names[mode], threads / 32, (double)h[0] / 2048,
                    e == cudaSuccess ? "" : cudaGetErrorString(e));
         }
+    printf("MMA (2 warps, N=16, 8 MMAs per unit) against concurrent tcgen05.st / tcgen05.ld warps\n");
+    long long h4[8];
+    for (int nacc : {4, 1})
+        for (int stw : {0, 4, 8, 12, 16})
+            for (int gap : {0, 4}) {
+                if (stw == 0 && gap) continue;
+                cudaMemset(cyc, 0, 64);
+                mma_vs_st<<<148, 640>>>(cyc, nacc, stw, 0, 2048, gap);
+                cudaError_t e = cudaDeviceSynchronize();
+                cudaMemcpy(h4, cyc, 64, cudaMemcpyDeviceToHost);
+                printf("  nacc=%d st_warps=%2d gap=%d: %7.1f cyc/unit per MMA warp; one st warp: %lld x 8 KB in %lld cyc (%.1f cyc / 8 KB) %s\n",
+                       nacc, stw, gap, (double)h4[0] / 2048, h4[2], h4[3], h4[2] ? (double)h4[3] / h4[2] : 0.0,
+                       e == cudaSuccess ? "" : cudaGetErrorString(e));
+            }
+    for (int ldw : {4, 8}) {
+        cudaMemset(cyc, 0, 64);
+        mma_vs_st<<<148, 640>>>(cyc, 4, 12, ldw, 2048, 0);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h4, cyc, 64, cudaMemcpyDeviceToHost);
+        printf("  nacc=4 st_warps=12 ld_warps=%d: %7.1f cyc/unit per MMA warp\n", ldw, (double)h4[0] / 2048);
+    }
     return 0;
 }

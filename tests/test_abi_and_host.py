@@ -173,3 +173,34 @@ def test_engines_refuse_states_without_room_for_the_tree():
     assert st._prefill(torch.zeros(1, 2048 - 40, dtype=torch.int64)) is False       # refused before any tensor work
     st.num_nodes = 1990
     assert st._append(torch.zeros(1, 20, dtype=torch.int64)) is False
+
+
+def test_checkpoint_reader_round_trip(tmp_path):
+    """models/checkpoint.py: a synthetic model written in the Hugging Face / AutoAWQ safetensors layout reads back
+    tensor-for-tensor, config.json gives the shape back, and a model without a checkpoint refuses to allocate
+    unless synthetic weights are asked for."""
+    import torch
+    from umbrella_b200.models import checkpoint as ck
+    from umbrella_b200.models import llama as L
+    from umbrella_b200.models.auto_model import AutoModelLM
+    shape = L.LlamaShape(hidden_size=256, intermediate_size=512, num_hidden_layers=3, num_attention_heads=4,
+                         num_key_value_heads=2, vocab_size=512, rope_scaling=None, rope_theta=10000.0)
+    for awq in (True, False):
+        d = str(tmp_path / ("awq" if awq else "fp16"))
+        ck.write_synthetic_checkpoint(d, shape, awq, seed=5, shard_layers=2)
+        got_shape, got_awq = ck.shape_from_config(d)
+        assert got_awq == awq and got_shape == shape
+        idx = ck.SafetensorsIndex(d)
+        head, ref_head = ck.read_head(idx, shape.tie_word_embeddings), L.synth_head(shape, 5)
+        assert all(torch.equal(head[k], ref_head[k]) for k in ("embed_tokens", "lm_head", "norm"))
+        for i in range(shape.num_hidden_layers):
+            w, ref = ck.read_layer(idx, i, awq), L.synth_layer(shape, i, awq, 5)
+            ck.check_layer_shapes(shape, w, awq, i)
+            for name in L.LINEAR_NAMES:
+                pairs = zip(w[name], ref[name]) if awq else [(w[name], ref[name])]
+                assert all(torch.equal(a, b) for a, b in pairs)
+            assert torch.equal(w["input_layernorm"], ref["input_layernorm"])
+    with pytest.raises(ck.CheckpointNotFound):
+        AutoModelLM.from_pretrained("meta-llama/Llama-3.2-1B-Instruct", max_length=64, device="cuda:0").alloc()
+    with pytest.raises(ValueError):
+        ck.check_layer_shapes(L.LLAMA32_1B, ck.read_layer(ck.SafetensorsIndex(d), 0, False), False, 0)

@@ -177,29 +177,28 @@ def test_lazy_leaf_kv_keeps_draft_quality():
 
 def test_append_after_lazily_skipped_leaf_row():
     """with lazy_leaf_kv the draft K/V row of an accepted last-level node is written by the NEXT
-    build_tree; a multi-turn ``_append`` in between must re-derive it.  Same scripted run with both schedules,
-    an append after every few iterations: identical tokens, and the draft cache rows agree (fp16 noise)."""
+    build_tree; a multi-turn ``_append`` in between must re-derive it.  After appends that follow leaf accepts, every
+    committed row of the draft cache must equal (fp16 noise) what a fresh causal pass over the same tokens gives --
+    a stale row (never written, or holding another tree node's K/V) is far outside that tolerance."""
+    from umbrella_b200.models.llama import SyntheticLlama
     from umbrella_b200.speculation.scripted import ScriptedAcceptance
     g = torch.Generator().manual_seed(31)
     prompt = torch.randint(3, TARGET.vocab_size, (1, 40), generator=g).to(DEV)
     extra = [torch.randint(3, TARGET.vocab_size, (1, 7), generator=g).to(DEV) for _ in range(3)]
-    caches, toks = [], []
-    for lazy in (False, True):
-        eng = _engine(draft_same=True, graph=False, lazy=lazy)
-        # accept whole chains (rank-0 child always accepted): the last-level node is accepted every iteration
-        eng.acceptance_script = ScriptedAcceptance(eng.Successors, seed=3, max_iters=64, device=DEV, acc=[1.0, 0.0, 0.0, 0.0])
-        assert eng._prefill(prompt)
-        for turn in range(3):
-            for _ in range(4):
-                eng.build_tree()
-                eng.verify()
-            assert eng.last_accept_length == eng.tree_depth      # a leaf was accepted: its draft row is pending
-            assert eng._append(extra[turn])
-        n = eng.num_nodes
-        toks.append(eng.tokens[0, :n + 1].cpu())
-        caches.append((eng.draft_model.kv_cache.k_cache[:, :n].float().cpu(),
-                       eng.draft_model.kv_cache.v_cache[:, :n].float().cpu()))
-        assert eng.draft_model.kv_cache.kv_offset == n == eng.target_model.kv_cache.kv_offset
-    assert torch.equal(toks[0], toks[1])
-    for a, b in zip(caches[0], caches[1]):
-        assert torch.allclose(a, b, atol=4e-3, rtol=2e-2)
+    eng = _engine(draft_same=True, graph=False, lazy=True)
+    # rank-0 children always accepted: the last-level node is accepted in every iteration
+    eng.acceptance_script = ScriptedAcceptance(eng.Successors, seed=3, max_iters=64, device=DEV, acc=[1.0, 0.0, 0.0, 0.0])
+    assert eng._prefill(prompt)
+    for turn in range(3):
+        for _ in range(4):
+            eng.build_tree()
+            eng.verify()
+        assert eng.last_accept_length == eng.tree_depth      # a leaf was accepted: its draft row is pending
+        assert eng._append(extra[turn])
+    n = eng.num_nodes
+    assert eng.draft_model.kv_cache.kv_offset == n == eng.target_model.kv_cache.kv_offset
+    fresh = SyntheticLlama(TARGET, max_length=384, awq=True, seed=21, device=DEV)
+    fresh.prefill_forward(eng.tokens[0, :n], torch.arange(n, device=DEV), want_logits=False)
+    for got, ref in ((eng.draft_model.kv_cache.k_cache, fresh.kv_cache.k_cache),
+                     (eng.draft_model.kv_cache.v_cache, fresh.kv_cache.v_cache)):
+        assert torch.allclose(got[:, :n].float(), ref[:, :n].float(), atol=6e-3, rtol=3e-2)

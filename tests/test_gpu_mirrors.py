@@ -113,3 +113,23 @@ def test_kv_cache_class_seams():
     assert cache.kv_offset == P + 3
     cache.clear()
     assert cache.kv_offset == 0 and float(cache.k_cache.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("awq", [True, False])
+def test_checkpoint_loader_equals_direct_weights(tmp_path, awq):
+    """safetensors on disk -> AutoModelLM.from_pretrained(<dir>).alloc() -> the same logits, bit for bit, as the
+    model fed the same tensors directly (umb_awq_repack is deterministic)."""
+    from umbrella_b200.models import checkpoint as ck
+    from umbrella_b200.models import llama as L
+    from umbrella_b200.models.auto_model import AutoModelLM
+    shape = L.LlamaShape(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, vocab_size=2048, rope_scaling=None, rope_theta=10000.0)
+    d = ck.write_synthetic_checkpoint(str(tmp_path / "m"), shape, awq, seed=9)
+    loaded = AutoModelLM.from_pretrained(d, max_length=128, device=DEV)
+    loaded.alloc()
+    assert loaded.weights_source == d and loaded.awq == awq
+    direct = L.SyntheticLlama(shape, max_length=128, awq=awq, seed=9, device=DEV)
+    ids = torch.randint(3, 2048, (37,), device=DEV)
+    a = loaded.prefill_forward(ids, torch.arange(37, device=DEV), last_only=False)
+    b = direct.prefill_forward(ids, torch.arange(37, device=DEV), last_only=False)
+    assert torch.equal(a, b)

@@ -66,10 +66,10 @@ def test_paged_equals_resident(awq, cache_layers, staging):
 def test_auto_model_keeps_fitting_models_resident():
     from umbrella_b200.models.auto_model import AutoModelLM
     m = AutoModelLM.from_pretrained("meta-llama/Llama-3.2-1B-Instruct", offload=True, max_length=256, device=DEV)
-    m.alloc(num_cache_layers=0)
+    m.alloc(num_cache_layers=0, synthetic=True)
     assert m.num_cache_layers == m.num_layers and not m._stage
     m2 = AutoModelLM.from_pretrained("meta-llama/Llama-3.2-1B-Instruct", offload=True, max_length=256, device=DEV)
-    m2.alloc(num_cache_layers=4, force_offload=True)
+    m2.alloc(num_cache_layers=4, force_offload=True, synthetic=True)
     assert m2.num_cache_layers == 4 and len(m2._stage) == 2
     ids = torch.randint(3, 30000, (40,), device=DEV)
     a = m.prefill_forward(ids, torch.arange(40, device=DEV))

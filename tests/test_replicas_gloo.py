@@ -26,6 +26,8 @@ def _worker(rank, world, port, out):
     # rank r "measured" (10 + 5 r) ms for (100 + r) tokens, e2e (2 + r) s for 50 tokens
     times, counts = replicas.reduce_over_replicas([10.0 + 5 * rank, 2.0 + rank], [100.0 + rank, 50.0])
     tput = replicas.aggregate_throughput([10.0 + 5 * rank], [100.0 + rank])
+    per = replicas.gather_over_replicas([7.0 + rank, 1.0])
+    assert per == [[7.0, 1.0], [8.0, 1.0]]                      # per-replica view (min / max in bench.py)
     dist.barrier()
     g = torch.Generator().manual_seed(replicas.replica_seed(7, rank))
     prompt = torch.randint(3, 30000, (8,), generator=g)
@@ -55,5 +57,6 @@ def test_two_replicas_reduce_like_bench():
 
 def test_single_process_is_identity():
     assert replicas.reduce_over_replicas([3.0], [4.0]) == ([3.0], [4.0])
+    assert replicas.gather_over_replicas([3.0, 4.0]) == [[3.0, 4.0]]
     assert replicas.assign_requests(5, 2) == [[0, 2, 4], [1, 3]]
     assert replicas.assign_requests(3, 8)[:3] == [[0], [1], [2]]

@@ -46,7 +46,7 @@ constexpr int kRecZeroOff = 8448;
 #define UMB_DQ_GROUPS 3
 #endif
 constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each, one per TMEM lane quarter)
-constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1);   // producer + 2 MMA issuers + dequant groups + epilogue group (AWQ)
+constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1) + 32;   // weight producer + 2 MMA issuers + dequant groups + epilogue group + x producer (AWQ)
 constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
 // Pipeline variants that were built, measured on B200 and rejected (sleeping mbarrier polls in the idle warps,
@@ -217,7 +217,9 @@ struct GemmParams {
     int* counters;                 // [tiles]
     float* slots;                  // [tiles + grid][MPAD][128]
     umb_rope_epilogue_t rope;      // UMB_EPI_ROPE_QKV operands (by value)
-    int stages;                    // depth of the shared-memory ring
+    int stages;                    // depth of the shared-memory ring (AWQ: of the weight-request ring)
+    int w_req;                     // AWQ: consecutive records per weight request
+    int x_slabs;                   // AWQ: depth of the x-slab ring
     unsigned long long* trace;     // debug timeline [grid][16] (UMB_GEMM_TRACE=1), else NULL
 };
 
@@ -230,13 +232,20 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // scripts/gemm_trace.py): even a predicated-off stamp costs issue slots inside the dequant loop.
 #ifdef UMB_GEMM_TRACE_BUILD
 #define UMB_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+// per-unit timeline of ONE CTA (UMB_UTRACE_CTA, default 0): [256 units][8 stamps] behind the per-CTA stamps
+#ifndef UMB_UTRACE_CTA
+#define UMB_UTRACE_CTA 0
+#endif
+#define UMB_UTRACE(unit, slot) do { if (p.trace && blockIdx.x == UMB_UTRACE_CTA && (unit) >= 0 && (unit) < 256) p.trace[8192 + (size_t)(unit) * 8 + (slot)] = gtimer(); } while (0)
 #else
 #define UMB_TRACE(slot) do { } while (0)
+#define UMB_UTRACE(unit, slot) do { } while (0)
 #endif
 
 template <int MPAD>
 struct GemmCfg {
-    static constexpr int kStagesAwq = MPAD == 16 ? 10 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4));
+    static constexpr int kStagesAwq = MPAD == 16 ? 6 : (MPAD == 32 ? 5 : 4);   // weight requests in flight (x kReqAwq records)
+    static constexpr int kReqAwq = 2;                                         // records per weight request
     static constexpr int kStagesF16 = MPAD <= 32 ? 8 : (MPAD == 64 ? 6 : 4);
     static constexpr int kXBytesAwq = MPAD * 256;           // [2 atoms][MPAD][128 B]
     static constexpr int kXBytesF16 = MPAD * 128;           // [MPAD][128 B]
@@ -249,10 +258,14 @@ struct GemmCfg {
     static constexpr int kNumAcc = MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : 2);
     static constexpr int kTmemACol0 = kNumAcc * MPAD < 128 ? 128 : kNumAcc * MPAD;   // A operand stages start here
     static constexpr int kTmemAStages = (kTmemCols - kTmemACol0) / 64;             // 6 (4 at MPAD = 128)
-    static constexpr int kBarBytes = 512;
-    static constexpr int smem_bytes(bool awq, int stages) {
+    static constexpr int kBarBytes = 768;
+    // AWQ: the weight ring holds `stages` requests of `req` consecutive records each (one cp.async.bulk per request);
+    // the x ring has one slab per tensor-memory A stage
+    __host__ __device__ static constexpr int w_stage_bytes(int req) { return (req * kRecordBytes + 127) / 128 * 128; }
+    static constexpr int kXSlabsAwq = MPAD == 16 ? 12 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4));
+    static constexpr int smem_bytes(bool awq, int stages, int req = 1, int x_slabs = kXSlabsAwq) {
         return 1024 /*align slack*/ + kBarBytes + kExchBytes +
-               stages * (awq ? (kXBytesAwq + kPackedStride) : (kXBytesF16 + kWBytesF16));
+               (awq ? x_slabs * kXBytesAwq + stages * w_stage_bytes(req) : stages * (kXBytesF16 + kWBytesF16));
     }
 };
 
@@ -544,13 +557,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* s_x = smem;                                   // kStages x kXBytes   (1024-aligned slabs)
-    unsigned char* s_w = s_x + kStages * kXBytes;                // kStages x kWStride
-    __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStride);
+    // AWQ: three rings -- weight requests (kStages x kReq consecutive records), x slabs (kXSlabs, one per unit) and
+    // the dequantised A operand in tensor memory (kAStages).  fp16: kStages stages of (x slab, weight tile).
+    const int kReq = kAwq ? p.w_req : 1;
+    const int kXSlabs = kAwq ? p.x_slabs : kStages;
+    const int kWStageBytes = kAwq ? Cfg::w_stage_bytes(kReq) : kWStride;
+    unsigned char* s_x = smem;                                   // kXSlabs x kXBytes   (1024-aligned slabs)
+    unsigned char* s_w = s_x + kXSlabs * kXBytes;                // kStages x kWStageBytes
+    __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStageBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes);
-    uint64_t* full_w = bars;                  // [kStages]   weight record / tile landed
-    uint64_t* full_x = bars + 16;             // [kStages]   x slab landed
-    uint64_t* done = bars + 32;               // [kStages]   every MMA of the unit in this stage has retired
+    uint64_t* full_w = bars;                  // [kStages]   weight request / tile landed
+    uint64_t* full_x = bars + 16;             // [kXSlabs]   x slab landed
+    uint64_t* done = bars + 32;               // AWQ: [kAStages] the MMAs reading this A stage have retired; fp16: [kStages]
+    uint64_t* w_empty = bars + 64;            // [kStages]   AWQ: every record of the request is in registers
+    uint64_t* x_done = bars + 80;             // [kXSlabs]   AWQ: the MMAs reading this x slab have retired
     uint64_t* a_full = bars + 48;             // [kAStages]  dequantised A operand is in tensor memory
     uint64_t* acc_full = bars + 56;
     uint64_t* acc_empty = bars + 57;
@@ -570,9 +590,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         if (!kAwq) tma_prefetch_desc(&tmap_w);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(full_w + i, 1);
-            mbar_init(full_x + i, 1);
-            mbar_init(done + i, 1);
+            mbar_init(w_empty + i, 4 * kReq);
         }
+        for (int i = 0; i < kXSlabs; ++i) {
+            mbar_init(full_x + i, 1);
+            mbar_init(x_done + i, 1);
+        }
+        for (int i = 0; i < (kAwq ? kAStages : kStages); ++i) mbar_init(done + i, 1);
         for (int i = 0; i < kAStages; ++i) mbar_init(a_full + i, 4);
         mbar_init(acc_full, 2);
         mbar_init(acc_empty, 4);
@@ -589,8 +613,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     const uint32_t tmem_base = *s_tmem;
     if (threadIdx.x == 0) UMB_TRACE(1);
 
-    if (warp == 0) {
-        // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    if (kAwq && warp == 0) {
+        // ===================== weight producer (AWQ) =====================
+        // One cp.async.bulk per REQUEST of kReq consecutive records: the issuing thread pays ~230 ns per request
+        // whatever its size (scripts/ubench/tma_rates.cu: 8.5 KB requests cap one SM at 37 GB/s = 5.4 TB/s for the
+        // chip, 17 KB requests at 71 GB/s), so single-record requests -- plus the x slab copies that used to share this
+        // loop -- were what held the stream at 0.6 of the HBM peak.  Weights never depend on the stream predecessor:
+        // no griddepcontrol.wait here, the ring fills while the previous kernel drains.
+        const uint64_t pol_w = l2_policy_evict_first();
+        const unsigned char* src = p.packed + u_begin * kRecordStride;
+        const int n_req = (n_units + kReq - 1) / kReq;
+        int ss = 0, round = 0;
+        for (int r = 0; r < n_req; ++r) {
+            if (round > 0) mbar_wait(w_empty + ss, (round - 1) & 1);
+            const int cnt = n_units - r * kReq < kReq ? n_units - r * kReq : kReq;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_w + ss, (uint32_t)(cnt * kRecordBytes));
+                tma_bulk_g2s(s_w + ss * kWStageBytes, src + (size_t)r * kReq * kRecordBytes, (uint32_t)(cnt * kRecordBytes),
+                             full_w + ss, pol_w);
+            }
+            __syncwarp();
+            if (lane == 0) UMB_UTRACE(r * kReq, 0);
+            if (++ss == kStages) {
+                ss = 0;
+                ++round;
+            }
+        }
+        if (lane == 0) UMB_TRACE(2);
+        if (lane == 0) UMB_TRACE(10);
+    } else if (kAwq && warp == kGemmThreads / 32 - 1) {
+        // ===================== x producer (AWQ): one slab per unit into the ring aligned with the TMEM A stages =====================
+        const uint64_t pol_x = l2_policy_evict_last();
+        pdl_wait();                                              // x is the predecessor's output
+        if (lane == 0) UMB_TRACE(3);
+        int g = in_tile0, xs = 0, round = 0;
+        for (int u = 0; u < n_units; ++u) {
+            if (round > 0) mbar_wait(x_done + xs, (round - 1) & 1);   // the unit that last used this slab has retired
+            if (lane == 0) UMB_UTRACE(u - kXSlabs, 6);
+            if (elect_one()) {
+                unsigned char* dst = s_x + xs * kXBytes;
+                mbar_arrive_expect_tx(full_x + xs, (uint32_t)kXBytes);
+                tma_tensor2d_g2s(dst, &tmap_x, g * kGroup, 0, full_x + xs, pol_x);
+                tma_tensor2d_g2s(dst + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full_x + xs, pol_x);
+            }
+            __syncwarp();
+            if (++g == p.units_per_tile) g = 0;
+            if (++xs == kXSlabs) {
+                xs = 0;
+                ++round;
+            }
+        }
+    } else if (warp == 0) {
+        // ===================== TMA producer, fp16 weights (whole warp runs the loop, one elected lane issues) =====================
         const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
         const unsigned char* src = p.packed + (kAwq ? u_begin * kRecordStride : 0);
         const int n_pre = n_units < kStages ? n_units : kStages;
@@ -636,6 +710,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         for (int i = 0; i < n_early; ++i) {                      // weights first: independent of the predecessor
             if (elect_one()) issue_w(i);
             __syncwarp();
+            if (lane == 0) UMB_UTRACE(i, 0);
             advance_w();
         }
         if (lane == 0) UMB_TRACE(2);
@@ -659,11 +734,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         r.phase = 1;                                             // every stage has been used once
         for (int i = n_pre; i < n_units; ++i) {
             mbar_wait(done + r.stage, r.phase ^ 1);              // the unit that last used this stage has retired
+            if (lane == 0) UMB_UTRACE(i - kStages, 6);
             if (elect_one()) {
                 issue_w(r.stage);
                 issue_x(r.stage, g);
             }
             __syncwarp();
+            if (lane == 0) UMB_UTRACE(i, 0);
             advance_w();
             r.advance(kStages);
         }
@@ -675,6 +752,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
         int st = par % kStages, ph = (par / kStages) & 1;            // smem ring position of unit `u`
         int ts = par % kAStages, pa = 0;                              // tensor-memory A ring position
+        int xsl = par % kXSlabs, xph = (par / kXSlabs) & 1;           // AWQ: x-slab ring position
         int u = par, seg = 0, seg_begin = 0, in_tile = in_tile0;
         while (seg_begin < n_units) {
             const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
@@ -685,24 +763,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const bool last = u + 2 >= seg_end;
                 if constexpr (kAwq) {
                     mbar_wait(a_full + ts, pa);
+                    mbar_wait(full_x + xsl, xph);
                 } else {
                     mbar_wait(full_w + st, ph);
+                    mbar_wait(full_x + st, ph);
                 }
-                mbar_wait(full_x + st, ph);
                 tc_fence_after();
                 if (u == 0 && lane == 0) UMB_TRACE(5);
-                const uint32_t xs = smem_u32(s_x + st * kXBytes);
+                if (lane == 0) UMB_UTRACE(u, 4);
+                const uint32_t xs = smem_u32(s_x + (kAwq ? xsl : st) * kXBytes);
                 const uint64_t bd0 = kDescHi | (uint64_t)((xs & 0x3FFFF) >> 4);
                 if constexpr (kAwq) {
                     const uint32_t a_col = tmem_base + kACol0 + ts * 64;
                     if (elect_one()) {
 #pragma unroll
+#ifdef UMB_EXP_MMA_COUNT   // timing-only experiment (wrong numerics): issue only the first UMB_EXP_MMA_COUNT MMAs of a unit
+                        for (int kk = 0; kk < UMB_EXP_MMA_COUNT; ++kk) {
+#else
                         for (int kk = 0; kk < 8; ++kk) {
+#endif
                             const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (MPAD * 128) + (kk & 3) * 32) >> 4);
                             umma_ts_f16(d_base + (kk % kAccHalf) * MPAD, a_col + kk * 8, bd, kIdesc,
                                         (first && kk < kAccHalf) ? 0u : 1u);
                         }
-                        umma_commit(done + st);
+                        umma_commit(done + ts);
+                        umma_commit(x_done + xsl);
                         if (last) umma_commit(acc_full);
                     }
                 } else {
@@ -718,6 +803,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     }
                 }
                 __syncwarp();
+                if (lane == 0) UMB_UTRACE(u, 5);
                 first = false;
                 st += 2;
                 while (st >= kStages) {
@@ -728,6 +814,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 if (ts >= kAStages) {
                     ts -= kAStages;
                     pa ^= 1;
+                }
+                xsl += 2;
+                if (xsl >= kXSlabs) {
+                    xsl -= kXSlabs;
+                    xph ^= 1;
                 }
             }
             if (first) {                     // this warp had no unit in the segment: plain arrival
@@ -748,34 +839,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         if (!is_epi) {
             // ===================== dequant warps (AWQ): group g takes CTA-local units g, g + kDqGroups, ... =====================
             if constexpr (kAwq) {
-                int dq_st = grp % kStages, dq_ph = 0, dq_ts = grp % kAStages;      // ring positions of unit `mine`
-                int w_first = grp;                                                 // first unit of this group that re-uses a TMEM stage
-                while (w_first < kAStages) w_first += kDqGroups;
-                int w_st = (w_first - kAStages) % kStages, w_ph = 0;               // ring position of unit `mine - kAStages`
-                // the packed words / scale / zero of a unit are pulled into registers as soon as its record has landed
+                // unit u lives in weight request u / kReq (ring slot (u / kReq) % kStages, record u % kReq inside it) and in
+                // x slab / tensor-memory A stage u % kAStages
                 uint4 w4[4];
                 uint32_t sbits = 0, zw = 0;
-                auto fetch = [&](int st_) {
-                    const uint32_t rec = smem_u32(s_w + st_ * kWStride);
+                int cur_ss = 0;
+                // the packed words / scale / zero of a unit are pulled into registers as soon as its request has landed
+                auto fetch = [&](int unit) {
+                    const int r = unit / kReq, round = r / kStages;
+                    cur_ss = r - round * kStages;
+                    mbar_wait(full_w + cur_ss, round & 1);
+                    if (q == 0 && lane == 0) UMB_UTRACE(unit, 1);
+                    const uint32_t rec = smem_u32(s_w + cur_ss * kWStageBytes + (unit - r * kReq) * kRecordBytes);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) w4[c] = lds128(rec + (c * kTileN + fl) * 16);    // 128 k of this feature row
                     sbits = lds16(rec + kRecScaleOff + fl * 2);
                     zw = lds32(rec + kRecZeroOff + (fl >> 3) * 4);
                 };
                 if (grp < n_units) {
-                    mbar_wait(full_w + dq_st, dq_ph);
+                    fetch(grp);
                     if (grp == 0 && q == 0 && lane == 0) UMB_TRACE(4);
-                    fetch(dq_st);
                 }
+                int ts = grp % kAStages, a_round = grp / kAStages;
                 for (int mine = grp; mine < n_units; mine += kDqGroups) {
-                    const int ts = dq_ts;
-                    dq_st += kDqGroups;
-                    if (dq_st >= kStages) {
-                        dq_st -= kStages;
-                        dq_ph ^= 1;
-                    }
-                    dq_ts += kDqGroups;
-                    if (dq_ts >= kAStages) dq_ts -= kAStages;
+                    const int ss = cur_ss;
                     const uint32_t z = (zw >> (4 * (fl & 7))) & 0xFu;
                     const __half2 ce = as_h2((0x6400u | z) * 0x10001u);                 // (1024 + z) x2
                     const __half2 neg_co = as_h2((0xD400u | (z << 4)) * 0x10001u);      // -(64 + z) x2
@@ -787,27 +874,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         const uint32_t words[4] = {w4[c].x, w4[c].y, w4[c].z, w4[c].w};
                         uint32_t a[16];
 #pragma unroll
+#ifdef UMB_EXP_NODQ         // timing-only experiment (wrong numerics): no dequant arithmetic, raw words go to tensor memory
+                        for (int w = 0; w < 4; ++w) { a[w * 4] = words[w]; a[w * 4 + 1] = words[w] ^ sbits; a[w * 4 + 2] = words[w] + z; a[w * 4 + 3] = ~words[w]; }
+#else
                         for (int w = 0; w < 4; ++w) dequant_word(words[w], magic, ce, neg_co, s2, &a[w * 4]);
-                        if (c == 0 && mine >= kAStages) {
+#endif
+                        if (c == 0 && a_round > 0) {
                             // the unit that last used this tensor-memory stage (mine - kAStages) must have retired
-                            mbar_wait(done + w_st, w_ph);
+                            if (q == 0 && lane == 0) UMB_UTRACE(mine, 2);
+                            mbar_wait(done + ts, (a_round - 1) & 1);
+                            if (q == 0 && lane == 0) UMB_UTRACE(mine, 7);
                             tc_fence_after();
-                            w_st += kDqGroups;
-                            if (w_st >= kStages) {
-                                w_st -= kStages;
-                                w_ph ^= 1;
-                            }
                         }
+#ifdef UMB_EXP_NOST         // timing-only experiment (wrong numerics): the A operand is never written to tensor memory
+                        if (a[0] == 0x12345678u && a[7] == 0x9abcdef0u) UMB_TMEM_ST_X16(taddr + c * 16, a);
+#else
                         UMB_TMEM_ST_X16(taddr + c * 16, a);
+#endif
                     }
+                    // every word of the record has been consumed: this warp's share of the request's ring slot is free
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(w_empty + ss);
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full + ts);
-                    if (mine + kDqGroups < n_units) {            // this group's next unit: (dq_st, dq_ph) already point at it
-                        mbar_wait(full_w + dq_st, dq_ph);
-                        fetch(dq_st);
+                    if (q == 0 && lane == 0) UMB_UTRACE(mine, 3);
+                    ts += kDqGroups;
+                    if (ts >= kAStages) {
+                        ts -= kAStages;
+                        ++a_round;
                     }
+                    if (mine + kDqGroups < n_units) fetch(mine + kDqGroups);     // this group's next unit
                 }
             }
         } else {
@@ -1117,6 +1215,21 @@ static unsigned long long* trace_buffer() {
     return buf;
 }
 
+// UMB_GEMM_TRACE_LAUNCH=k: stamp only the k-th launch (0-based) after the last umb_debug_gemm_trace read, so that a
+// launch in the middle of a back-to-back chain can be looked at without its neighbours overwriting the stamps
+static int g_trace_launches = 0;
+static unsigned long long* trace_for_this_launch() {
+    unsigned long long* buf = trace_buffer();
+    if (!buf) return nullptr;
+    static int want = -2;
+    if (want == -2) {
+        const char* e = getenv("UMB_GEMM_TRACE_LAUNCH");
+        want = e ? atoi(e) : -1;
+    }
+    const int idx = g_trace_launches++;
+    return (want < 0 || idx == want) ? buf : nullptr;
+}
+
 // rows one launch takes (see gemm_common); 128 with UMB_GEMM_ALLOW_128=1
 static int max_rows_per_launch() {
     static int cached = 0;
@@ -1132,16 +1245,29 @@ static int mpad_of(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 
 template <int MPAD, bool kAwq>
 static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, GemmParams p, int grid, cudaStream_t st) {
     p.stages = kAwq ? GemmCfg<MPAD>::kStagesAwq : GemmCfg<MPAD>::kStagesF16;
+    p.w_req = kAwq && kRecordStride == kRecordBytes ? GemmCfg<MPAD>::kReqAwq : 1;   // multi-record requests need a gap-free stream
+    p.x_slabs = GemmCfg<MPAD>::kXSlabsAwq;
     {
-        static int env_stages = -1;
+        static int env_stages = -1, env_req = -1, env_xs = -1;   // tuning switches: UMB_GEMM_STAGES, UMB_GEMM_WREQ, UMB_GEMM_XSLABS
         if (env_stages < 0) {
             const char* e = getenv("UMB_GEMM_STAGES");
             env_stages = e ? atoi(e) : 0;
+            e = getenv("UMB_GEMM_WREQ");
+            env_req = e ? atoi(e) : 0;
+            e = getenv("UMB_GEMM_XSLABS");
+            env_xs = e ? atoi(e) : 0;
         }
-        if (env_stages > 0 && env_stages <= 16 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024) p.stages = env_stages;
+        const int st = env_stages > 0 && env_stages <= 16 ? env_stages : p.stages;
+        const int rq = kAwq && env_req > 0 && env_req <= 16 && kRecordStride == kRecordBytes ? env_req : p.w_req;
+        const int xs = kAwq && env_xs >= 2 && env_xs <= 16 ? env_xs : p.x_slabs;
+        if ((st != p.stages || rq != p.w_req || xs != p.x_slabs) && GemmCfg<MPAD>::smem_bytes(kAwq, st, rq, xs) <= 227 * 1024) {
+            p.stages = st;
+            p.w_req = rq;
+            p.x_slabs = xs;
+        }
     }
-    p.trace = trace_buffer();
-    const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages);
+    p.trace = trace_for_this_launch();
+    const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages, p.w_req, p.x_slabs);
     static int attr_smem = 0;
     if (attr_smem < smem) {
         UMB_CUDA(cudaFuncSetAttribute(gemm_kernel<MPAD, kAwq>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1351,6 +1477,8 @@ extern "C" int umb_debug_gemm_trace(unsigned long long* host_out, int max_ctas) 
     if (max_ctas > 1024) max_ctas = 1024;
     UMB_CUDA(cudaDeviceSynchronize());
     UMB_CUDA(cudaMemcpy(host_out, buf, (size_t)max_ctas * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    UMB_CUDA(cudaMemset(buf, 0, 1024 * 16 * sizeof(unsigned long long)));
+    g_trace_launches = 0;
     return UMB_OK;
 }
 

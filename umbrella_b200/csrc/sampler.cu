@@ -19,14 +19,15 @@
 //   1. seen-token bitmap in shared memory (the penalty's gather / scatter is idempotent per token id)
 //   2. exact k-th largest value by a 4-pass radix select over orderable keys (ties at the k-th value all stay,
 //      as `logits < kth` / top_k_mask_logits keep them)
-//   3. the <= 1024 survivors (index order) in shared memory; softmax, nucleus test and the draw run on them.
+//   3. the survivors (top_k <= 1024 plus ties, <= 2048; index order) in shared memory; softmax, nucleus test and the draw run on them.
 #include "common.cuh"
 #include "internal.h"
 
 namespace umb {
 
 constexpr int kSampleThreads = 1024;
-constexpr int kSurvivorCap = 1024;
+constexpr int kMaxTopK = 1024;
+constexpr int kSurvivorCap = 2048;      // top_k + ties at the k-th value (fp16-valued logits tie often)
 
 __device__ __forceinline__ uint32_t orderable_key(float f) {
     const uint32_t u = __float_as_uint(f);
@@ -144,12 +145,12 @@ __global__ void __launch_bounds__(kSampleThreads, 1) sample_kernel(const SampleP
     }
     __syncthreads();
     const int n = s_count < kSurvivorCap ? s_count : kSurvivorCap;   // > cap only for degenerate rows (mass ties)
-    if (tid < n) {
-        const int mine = s_tmp_idx[tid];
+    for (int t = tid; t < n; t += kSampleThreads) {
+        const int mine = s_tmp_idx[t];
         int rank = 0;
         for (int j = 0; j < n; ++j) rank += s_tmp_idx[j] < mine;
         s_idx[rank] = mine;
-        s_val[rank] = s_tmp_val[tid];
+        s_val[rank] = s_tmp_val[t];
     }
     __syncthreads();
     // ---- softmax over the survivors (everything else is exp(-inf) = 0 in the reference), fixed summation order
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kSampleThreads, 1) sample_kernel(const SampleP
         s_max = m;
     }
     __syncthreads();
-    if (tid < n) s_val[tid] = expf(s_val[tid] - s_max);
+    for (int t = tid; t < n; t += kSampleThreads) s_val[t] = expf(s_val[t] - s_max);
     __syncthreads();
     if (tid == 0) {
         float z = 0.f;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kSampleThreads, 1) sample_kernel(const SampleP
         s_sum = z;
     }
     __syncthreads();
-    if (tid < n) s_val[tid] = s_val[tid] / s_sum;
+    for (int t = tid; t < n; t += kSampleThreads) s_val[t] = s_val[t] / s_sum;
     __syncthreads();
 
     if (p.mode == UMB_SAMPLE_STATIC) {
@@ -203,11 +204,11 @@ __global__ void __launch_bounds__(kSampleThreads, 1) sample_kernel(const SampleP
         return;
     }
     // ---- dynamic: top_p_renorm_prob's kept set {j : mass(probs > probs[j]) < top_p}, then the inverse CDF
-    if (tid < n) {
-        const float mine = s_val[tid];
+    for (int t = tid; t < n; t += kSampleThreads) {
+        const float mine = s_val[t];
         float gt = 0.f;
         for (int j = 0; j < n; ++j) gt += s_val[j] > mine ? s_val[j] : 0.f;
-        s_keep[tid] = gt < p.top_p;
+        s_keep[t] = gt < p.top_p;
     }
     __syncthreads();
     if (tid == 0) {
@@ -256,7 +257,7 @@ extern "C" int umb_sample_f32(const float* logits, int64_t ld, int rows, int voc
     if (mode != UMB_SAMPLE_ARGMAX) {
         UMB_CHECK_ARG(uniforms && temperature > 0.f && top_k >= 1 && top_p > 0.f);
         UMB_CHECK_ARG(mode == UMB_SAMPLE_DYNAMIC || rounds >= 1);
-        if (top_k > umb::kSurvivorCap) return UMB_ERR_UNSUPPORTED;
+        if (top_k > umb::kMaxTopK) return UMB_ERR_UNSUPPORTED;
         p.inv_t = 1.f / temperature;
         p.top_k = top_k;
         p.top_p = top_p;
@@ -265,8 +266,8 @@ extern "C" int umb_sample_f32(const float* logits, int64_t ld, int rows, int voc
     }
     const size_t smem = p.pen_ids ? (size_t)((vocab + 31) / 32) * 4 : 0;
     if (smem > 160 * 1024) return UMB_ERR_UNSUPPORTED;
-    if (smem > 16 * 1024)
-        UMB_CUDA(cudaFuncSetAttribute(umb::sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 0)   // ~36 KB of static shared memory + the bitmap exceed the 48 KB default: opt in (per device, cheap)
+        UMB_CUDA(cudaFuncSetAttribute(umb::sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     UMB_LAUNCH_PDL(umb::sample_kernel, dim3(rows), dim3(umb::kSampleThreads), smem, (cudaStream_t)stream, p);
     umb::count_launches(1);
     return UMB_OK;

@@ -1,11 +1,16 @@
 """AutoModelLM: name -> model class (mirror of reference umbrella/models/auto_model.py:9-182 for the
 Llama entries; the Qwen/Mistral/Gemma tables are out of scope).
 
-There are no checkpoints (and no network) in this environment, so ``alloc()`` of a model built by
-name attaches *synthetic* weights of that architecture unless a loader has attached real tensors
-(``load_head`` / ``load_awq_layer`` / ``load_fp16_layer``) -- SURVEY.md 8d.
+``alloc()`` loads the model's safetensors checkpoint (fp16 or AutoAWQ INT4) from a local directory or the Hugging
+Face cache through models/checkpoint.py -- no ``autoawq`` / ``gptqmodel`` needed -- and raises ``CheckpointNotFound``
+when there is none.  Synthetic seeded weights of the architecture (there are no real weights and no network in this
+environment) are strictly opt-in: ``alloc(synthetic=True)`` or a ``"synthetic": true`` /
+``"synthetic_seed": N`` key in the engine config.  ``model_name`` may also be a checkpoint directory of a Llama
+architecture that is not in the table (its config.json supplies the shape).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -29,6 +34,9 @@ def _weight_bytes(shape, awq: bool) -> int:
 
 def _make(model_name, offload=False, batch_size=1, max_length=256, device="cuda:0", dtype=torch.float16, **unused):
     entry = L.KNOWN_MODELS.get(model_name)
+    if entry is None and os.path.isfile(os.path.join(str(model_name), "config.json")):
+        from .checkpoint import shape_from_config
+        entry = shape_from_config(model_name)          # a local Llama-architecture checkpoint directory
     if entry is None:
         raise ValueError(f"Model type '{model_name}' is not supported. "
                          f"Supported types: {[k for k, v in L.KNOWN_MODELS.items() if v]}")
@@ -44,8 +52,17 @@ def _make(model_name, offload=False, batch_size=1, max_length=256, device="cuda:
     def alloc(**kwargs):
         """Reference ``alloc(**config)`` reads num_cache_layers / exit_layer (llama.py:153,328,421)."""
         exit_layer = kwargs.get("exit_layer")
+        synthetic = bool(kwargs.get("synthetic", False)) or "synthetic_seed" in kwargs
         seed = kwargs.get("synthetic_seed", 1234)
         gen_device = kwargs.get("synthetic_gen_device", str(model.device))
+        ckpt = None
+        if not synthetic:
+            from .checkpoint import CheckpointNotFound, resolve_checkpoint
+            try:
+                ckpt = resolve_checkpoint(model_name)
+            except CheckpointNotFound as e:
+                raise CheckpointNotFound(f"{e}  Pass synthetic=True (engine config: \"synthetic\": true) to run "
+                                         f"seeded random weights of this architecture instead.") from None
         if exit_layer is not None and not awq and 0 < exit_layer < model.num_layers:
             model.num_layers = exit_layer              # draft truncation (llama.py:421,450-451)
         if offload:
@@ -58,11 +75,16 @@ def _make(model_name, offload=False, batch_size=1, max_length=256, device="cuda:
             base_alloc(**kwargs)
         else:
             base_alloc()
-        head = L.synth_head(shape, seed, gen_device)
-        model.load_head(head["embed_tokens"], head["lm_head"], head["norm"])
-        for i in range(model.num_layers):
-            w = L.synth_layer(shape, i, awq, seed, gen_device)
-            (model.load_awq_layer if awq else model.load_fp16_layer)(i, w)
+        if ckpt is not None:
+            from .checkpoint import load_checkpoint
+            load_checkpoint(model, ckpt, awq)
+        else:
+            head = L.synth_head(shape, seed, gen_device)
+            model.load_head(head["embed_tokens"], head["lm_head"], head["norm"])
+            for i in range(model.num_layers):
+                w = L.synth_layer(shape, i, awq, seed, gen_device)
+                (model.load_awq_layer if awq else model.load_fp16_layer)(i, w)
+        model.weights_source = ckpt or f"synthetic(seed={seed})"
         torch.cuda.synchronize(model.device)
         return model
 
@@ -76,7 +98,7 @@ class AutoModelLM:
 
     @classmethod
     def from_pretrained(cls, model_name, offload=False, cuda_graph=False, **kwargs):
-        if model_name not in cls._MODEL_MAPPING:
+        if model_name not in cls._MODEL_MAPPING and not os.path.isfile(os.path.join(str(model_name), "config.json")):
             raise ValueError(f"Model type '{model_name}' is not supported. "
                              f"Supported types: {list(cls._MODEL_MAPPING.keys())}")
         # offload=True -> the paged classes of models/offload.py (LlamaOffload / LlamaAwqOffload);

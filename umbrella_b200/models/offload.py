@@ -103,6 +103,10 @@ class _Paged:
                 sum(t.numel() * t.element_size() for t in lw.values())
         return n
 
+    def paged_bytes_per_forward(self) -> int:
+        """Host -> device bytes one forward moves (every offloaded layer's slab once)."""
+        return sum(lw["host_slab"].numel() for lw in self.layer_weights if lw is not None and "host_slab" in lw)
+
     # ------------------------------------------------------------------ paging
     def _enqueue_load(self, b: int, j: int):
         """Copy offloaded layer j into staging slab b on the side stream, after the slab's last reader."""

@@ -44,6 +44,18 @@ def reduce_over_replicas(times: list[float], counts: list[float], device=None):
     return t.tolist(), c.tolist()
 
 
+def gather_over_replicas(values: list[float], device=None) -> list[list[float]]:
+    """Every replica's ``values`` (one list per rank, rank order) -- the per-replica min / max SURVEY.md 8e asks for."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [list(map(float, values))]
+    t = torch.tensor(values, dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [o.tolist() for o in out]
+
+
 def aggregate_throughput(times_ms: list[float], counts: list[float], device=None) -> float:
     """Units all ranks processed / the slowest rank's time (units per second)."""
     t, c = reduce_over_replicas(times_ms, counts, device)
