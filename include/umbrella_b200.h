@@ -235,6 +235,12 @@ int umb_sample_f32(const float* logits, int64_t ld, int rows, int vocab, int mod
                    float top_p, const float* uniforms, int rounds, const int64_t* penalty_ids, int penalty_count,
                    const int32_t* penalty_count_dev, float penalty, int64_t* out, umb_stream_t stream);
 
+/* Row-wise top-k of fp32 logits [rows, vocab], sorted by value descending (lower token id first among equal values):
+ * out_vals fp32 [rows, k], out_ids int64 [rows, k].  Replaces ``logits.topk(k)`` on the draft side
+ * (speculation_utils.py:52-61 sampling_argmax_gather, dynamic_speculation_engine.py:235).  k <= 64. */
+int umb_topk_f32(const float* logits, int64_t ld, int rows, int vocab, int k, float* out_vals, int64_t* out_ids,
+                 umb_stream_t stream);
+
 /* decode the UMB_EPI_LOGITS arg-max keys into int64 token ids */
 int umb_argmax_keys_to_ids(const unsigned long long* keys, int rows, int64_t* out, umb_stream_t stream);
 
@@ -334,6 +340,10 @@ int umb_llama_forward_dyn(const umb_llama_t* model, const int64_t* tokens_base, 
 /* tokens_base[n_dev[0] + offset + i] = src[i], i < count  (draft tokens of the next tree level) */
 int umb_store_tokens(int64_t* tokens_base, const int32_t* n_dev, int offset, const int64_t* src, int count,
                      int capacity, umb_stream_t stream);
+/* same with a gather: tokens_base[n + offset + i] = src[gather[i]]  (n = n_dev[0], or num_nodes when n_dev is NULL):
+ * the growmap-ordered pick of the per-node top-k draft tokens (static_speculation_engine.py:115-123, 279-281) */
+int umb_store_tokens_gather(int64_t* tokens_base, const int32_t* n_dev, int num_nodes, int offset, const int64_t* src,
+                            const int64_t* gather, int count, int capacity, umb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -27,9 +27,10 @@ for (K, N, mode, name) in ((8192, 57344, ops.UMB_EPI_SILU_MUL, "gate|up"), (8192
     _lib.check(_lib.load().umb_debug_gemm_trace(buf.ctypes.data_as(C.c_void_p), 1024))
     t = buf.reshape(-1)[8192:8192 + 256 * 8].reshape(256, 8).astype(np.int64)
     n_units = int((t[:, 5] > 0).sum())
+    np.save(os.path.join(ROOT, "gpurun_out", f"unit_trace_{name.replace('|', '')}_M{M}.npy"), t[:n_units])
     t0 = t[0, 0]
     print(f"== {name} M={M}: CTA 0, {n_units} units; times in ns relative to the first TMA issue")
-    print("unit   w_issue  landed  dq_first  tmem_free  a_full   mma_go  mma_done_issue  retired_seen | a_full-landed  mma_go-a_full  issue_dur  per-unit")
+    print("unit   w_issue  landed  mma>a_full mma>full_x  a_full   mma_go  mma_done_issue  retired_seen | a_full-landed  mma_go-a_full  issue_dur  per-unit   (drain build: columns 3/4 are MMA-warp stamps)")
     prev = None
     for u in range(n_units):
         r = t[u]

@@ -41,10 +41,12 @@ def available() -> str | None:
     return None
 
 
-def awq_linear(x: torch.Tensor, triplet) -> torch.Tensor:
-    """AwqLinear.apply for fewer than 1024 rows (awq_utils.py:74-77)."""
+def awq_linear(x: torch.Tensor, w) -> torch.Tensor:
+    """AwqLinear.apply for fewer than 1024 rows (awq_utils.py:74-77); fp16 models: F.linear (llama.py:87-110)."""
+    if isinstance(w, torch.Tensor):
+        return torch.nn.functional.linear(x, w)
     from vllm import _custom_ops as vops
-    qweight, qzeros, scales = triplet
+    qweight, qzeros, scales = w
     return vops.awq_gemm(x.reshape(-1, x.shape[-1]).contiguous(), qweight, scales, qzeros, 8)
 
 
@@ -99,3 +101,41 @@ def layer_forward(shape, raw: dict, hidden, position_ids, mask, k_layer, v_layer
 def final_logits(shape, hidden, norm_weight, lm_head):
     """llama.py:316-322."""
     return torch.nn.functional.linear(rmsnorm(hidden, norm_weight, shape.rms_norm_eps), lm_head).float()
+
+
+def three_way_logits(L, ollama, shape, oshape, awq: bool, seed: int, layers: int, prompt, tree_tokens, pos_p, pos_t, causal,
+                     dense, cos, sin, device, on_layer=None, max_length: int = 256):
+    """Stream ``layers`` synthetic decoder layers (models/llama.py synth_layer, generated on ``device``) through three
+    implementations -- the fp32 oracle with the reference's fp16 rounding points and fp16-rounded weights, the same with
+    exact (unrounded) weights, and the reference's own kernels -- over a causal prefill of the prompt rows followed by the
+    tree rows.  ``on_layer(l, raw)`` lets the caller feed the same tensors to the product model.  Returns the tree-row
+    logits {"oracle", "oracle_exact", "reference" (None when the kernels are unavailable)} and the head tensors."""
+    head = L.synth_head(shape, seed, gen_device=device)
+    lm_head = head["embed_tokens"] if head["lm_head"] is None else head["lm_head"]
+    why = available()
+    emb_p = torch.nn.functional.embedding(prompt, head["embed_tokens"])
+    emb_t = torch.nn.functional.embedding(tree_tokens, head["embed_tokens"])
+    h16, hx, hr = [emb_p.clone(), emb_t.clone()], [emb_p.clone(), emb_t.clone()], [emb_p[0].clone(), emb_t[0].clone()]
+    hkv, d, P = shape.num_key_value_heads, shape.head_dim, prompt.shape[1]
+    for l in range(layers):
+        raw = L.synth_layer(shape, l, awq, seed, gen_device=device)
+        if on_layer is not None:
+            on_layer(l, raw)
+        for hs, exact in ((h16, False), (hx, True)):
+            w = ollama.oracle_layer_weights(raw, 128, awq, exact=exact)
+            k_l = torch.zeros(max_length, hkv, d, dtype=torch.float16, device=device)
+            v_l = torch.zeros_like(k_l)
+            hs[0] = ollama.layer_forward(oshape, w, hs[0], pos_p, causal, k_l, v_l, 0, cos, sin)
+            hs[1] = ollama.layer_forward(oshape, w, hs[1], pos_t, dense, k_l, v_l, P, cos, sin)
+            del w
+        if why is None:
+            k_l = torch.zeros(max_length, hkv, d, dtype=torch.float16, device=device)
+            v_l = torch.zeros_like(k_l)
+            hr[0] = layer_forward(oshape, raw, hr[0], pos_p[0], causal, k_l, v_l, 0, cos, sin)
+            hr[1] = layer_forward(oshape, raw, hr[1], pos_t[0], dense, k_l, v_l, P, cos, sin)
+        del raw
+    out = {"oracle": ollama.final_logits(oshape, h16[1], head["norm"], lm_head)[0],
+           "oracle_exact": ollama.final_logits(oshape, hx[1], head["norm"], lm_head)[0],
+           "reference": final_logits(oshape, hr[1], head["norm"], lm_head) if why is None else None,
+           "reference_unavailable": why, "head": head}
+    return out

@@ -77,3 +77,46 @@ def test_auto_model_keeps_fitting_models_resident():
     assert torch.equal(a, b)
     with pytest.raises(ValueError):
         AutoModelLM.from_pretrained("no/such-model")
+
+
+def test_kv_host_pages_equal_resident_cache():
+    """Host-resident KV pages (models/kv_paging.py): the K/V planes of the upper layers live in pinned host memory and
+    stream through two staging planes.  Same kernels, same bytes -> prefill logits, every verify and the committed
+    tokens are bit-identical to the fully resident model, and after the run the host planes hold exactly the rows the
+    resident cache holds (accept-path compaction included)."""
+    from oracle import llama as ollama
+    from umbrella_b200.models.llama import SyntheticLlama
+    from umbrella_b200.speculation.scripted import ScriptedAcceptance
+    from umbrella_b200.speculation.static_speculation_engine import StaticSpeculationEngine
+    shape = ollama.LlamaShape(hidden_size=512, intermediate_size=1024, num_hidden_layers=5, num_attention_heads=4,
+                              num_key_value_heads=2, vocab_size=2048, rope_scaling=None, rope_theta=10000.0)
+    S = 512
+    g = torch.Generator().manual_seed(3)
+    prompt = torch.randint(3, shape.vocab_size, (1, 150), generator=g).to(DEV)      # > 64 rows: chunked prefill
+    runs = []
+    for host_layers in (0, 3):
+        eng = StaticSpeculationEngine("draft", "target", device=DEV, growmap_path="sequoia_tree-3x4.json", max_length=S,
+                                      safe_buffer=48, graph_iteration=False)
+        target = SyntheticLlama(shape, max_length=S, awq=True, seed=5, device=DEV, kv_host_layers=host_layers)
+        draft = SyntheticLlama(shape, max_length=S, awq=True, seed=5, device=DEV)
+        eng.initialize(draft_model=draft, target_model=target)
+        eng._set_eos([])
+        eng.acceptance_script = ScriptedAcceptance(eng.Successors, seed=4, max_iters=64, device=DEV)
+        assert eng._prefill(prompt)
+        for _ in range(12):
+            eng.build_tree()
+            eng.verify()
+        n = eng.num_nodes
+        kc = target.kv_cache
+        if host_layers:
+            kc.apply_pending_gather()
+            assert kc.k_cache.shape[0] == shape.num_hidden_layers - host_layers + 2
+            k = torch.cat([kc.k_cache[:kc.resident_layers, :n].cpu(), kc.k_host[:, :n]], 0)
+            v = torch.cat([kc.v_cache[:kc.resident_layers, :n].cpu(), kc.v_host[:, :n]], 0)
+            stats = target.kv_paging_stats()
+            assert stats["kv_host_layers"] == 3 and stats["h2d_bytes_per_forward"] > 0
+        else:
+            k, v = kc.k_cache[:, :n].cpu(), kc.v_cache[:, :n].cpu()
+        runs.append((eng.tokens[0, :n + 1].cpu(), k, v))
+    assert torch.equal(runs[0][0], runs[1][0])
+    assert torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])

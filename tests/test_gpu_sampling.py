@@ -148,3 +148,29 @@ def test_engine_stochastic_verify_is_the_oracle_algorithm(engine_kind):
         assert checked > 0.9 * sum(len(s[3]) for s in seen)
         outs.append(eng.tokens[0, :eng.num_nodes + 1].cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("rows,vocab,k", [(1, 128256, 4), (13, 128256, 24), (64, 32000, 64), (3, 1000, 1)])
+def test_topk_kernel_equals_torch(rows, vocab, k):
+    """umb_topk_f32 against torch.topk: same values; same ids wherever the value is unique in the row (equal values:
+    lower token id first, torch leaves that order unspecified)."""
+    from umbrella_b200 import ops
+    x, _ = _logits(rows, vocab, 11 * rows + k, fp16_grid=(rows % 2 == 1))
+    xd = torch.from_numpy(x).to(DEV)
+    vals, ids = ops.topk(xd, k)
+    tv, ti = xd.topk(k, dim=-1)
+    assert torch.equal(vals, tv)
+    assert torch.equal(xd.gather(1, ids), vals)                       # every id points at its value
+    uniq = torch.ones_like(tv, dtype=torch.bool)
+    uniq[:, 1:] &= tv[:, 1:] != tv[:, :-1]
+    uniq[:, :-1] &= tv[:, :-1] != tv[:, 1:]
+    assert torch.equal(ids[uniq], ti[uniq])
+    srt = ids.clone()
+    for r in range(rows):                                            # among equals: ascending token id
+        for j in range(1, k):
+            if vals[r, j] == vals[r, j - 1]:
+                assert int(srt[r, j]) > int(srt[r, j - 1])
+    toks = torch.zeros(256, dtype=torch.int64, device=DEV)
+    gather = torch.randint(0, rows * k, (min(40, rows * k),), device=DEV)
+    ops.store_tokens_gather(toks, ids, gather, 7, num_nodes=100)
+    assert torch.equal(toks[107:107 + gather.numel()], ids.flatten()[gather])

@@ -95,6 +95,8 @@ SIGNATURES = {
                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "umb_sample_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p, c_int, c_void_p,
                                c_int, c_void_p, c_float, c_void_p, c_void_p]),
+    "umb_topk_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "umb_store_tokens_gather": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "umb_store_tokens": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "umb_dyn_tree_expand": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),

@@ -33,9 +33,12 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None, variant: str = "") -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None, variant: str = "",
+          gemm_source: str | None = None) -> str:
     """``variant`` + ``extra_flags`` (e.g. ["-DUMB_DQ_GROUPS=4"]) build an experiment library
-    libumbrella_b200.<variant>.so next to the product one; select it with UMB_LIB_PATH."""
+    libumbrella_b200.<variant>.so next to the product one; select it with UMB_LIB_PATH.  ``gemm_source`` swaps
+    csrc/gemm.cu for another translation unit exporting the same entry points (csrc/experimental/gemm_ring.cu: the
+    round-2 weight-request-ring / drain-form kernel, kept for the experiments recorded in profiles/r2_gemm_experiments.txt)."""
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + list(extra_flags or [])
     obj_dir = os.path.join(HERE, "build" + (("_" + variant) if variant else ""))
@@ -46,11 +49,11 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
     objs = []
     procs = []
     for s in srcs:
-        src = os.path.join(CSRC, s)
+        src = os.path.join(CSRC, gemm_source if (gemm_source and s == "gemm.cu") else s)
         obj = os.path.join(obj_dir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + flags + ["-c", src, "-o", obj]
+            cmd = [nvcc] + flags + ["-I", CSRC, "-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -72,5 +75,6 @@ if __name__ == "__main__":
     # python -m umbrella_b200.build [--force] [--variant NAME -DFOO=1 ...]
     argv = sys.argv[1:]
     variant = argv[argv.index("--variant") + 1] if "--variant" in argv else ""
+    gemm = argv[argv.index("--gemm") + 1] if "--gemm" in argv else None
     print(build(force="--force" in argv, verbose=True, extra_flags=[a for a in argv if a.startswith("-D")],
-                variant=variant))
+                variant=variant, gemm_source=gemm))

@@ -46,9 +46,18 @@ constexpr int kRecZeroOff = 8448;
 #define UMB_DQ_GROUPS 3
 #endif
 constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each, one per TMEM lane quarter)
-constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1);   // producer + 2 MMA issuers + dequant groups + epilogue group (AWQ)
+constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1) + 32;   // weight producer + 2 MMA issuers + dequant groups + epilogue group + x producer (AWQ)
 constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
+// AWQ "drain" form (default): the dequant warps feed the MMA the EXACT integers (q - z) -- one lop3 and one exact
+// hsub2 / hfma2 per nibble pair, no multiply -- every 128-k unit accumulates into its own tensor-memory accumulator, and
+// the epilogue warps drain it as acc += s[g, n] * D_g[n, :] in fp32.  That halves the fp16x2 work of the dequant warps,
+// which is what paced the kernel (profiles/r2_gemm_experiments.txt), and applies the group scale once in fp32 instead of
+// rounding every weight to fp16 first.  UMB_AWQ_DRAIN=0 builds the previous form (fp16((q - z) * s) operands).
+#ifndef UMB_AWQ_DRAIN
+#define UMB_AWQ_DRAIN 1
+#endif
+constexpr int kScaleRing = 16;           // drain form: group scales of the units in flight, [kScaleRing][128] fp32 in smem
 // Pipeline variants that were built, measured on B200 and rejected (sleeping mbarrier polls in the idle warps,
 // software-pipelined dequant, x slabs ahead of the weight ring, early residual fetch / early partial-sum
 // reduction, a fourth dequant group) are recorded in profiles/r1_gemm_experiments.txt; none beat this form,
@@ -184,6 +193,15 @@ __device__ __forceinline__ void dequant_word(uint32_t w, uint32_t magic, __half2
     out[2] = as_u32(__hmul2(__hsub2(as_h2(lop3_and_or<0x000f000fu>(w8, magic)), ce), s2));
     out[3] = as_u32(__hmul2(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w8, magic)), sixteenth, neg_co), s2));
 }
+// drain form: the exact integers (q - z) as fp16 pairs, no scale
+__device__ __forceinline__ void dequant_word_int(uint32_t w, uint32_t magic, __half2 ce, __half2 neg_co, uint32_t* out) {
+    const __half2 sixteenth = as_h2(0x2C002C00u);                 // 1/16
+    const uint32_t w8 = w >> 8;
+    out[0] = as_u32(__hsub2(as_h2(lop3_and_or<0x000f000fu>(w, magic)), ce));
+    out[1] = as_u32(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w, magic)), sixteenth, neg_co));
+    out[2] = as_u32(__hsub2(as_h2(lop3_and_or<0x000f000fu>(w8, magic)), ce));
+    out[3] = as_u32(__hfma2(as_h2(lop3_and_or<0x00f000f0u>(w8, magic)), sixteenth, neg_co));
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -217,7 +235,11 @@ struct GemmParams {
     int* counters;                 // [tiles]
     float* slots;                  // [tiles + grid][MPAD][128]
     umb_rope_epilogue_t rope;      // UMB_EPI_ROPE_QKV operands (by value)
-    int stages;                    // depth of the shared-memory ring
+    int stages;                    // depth of the shared-memory ring (AWQ: of the weight-request ring)
+    int w_req;                     // AWQ: consecutive records per weight request
+    int x_slabs;                   // AWQ: depth of the x-slab ring
+    const __half* x;               // AWQ drain form: the dequant warps stage the x slabs themselves
+    int64_t ldx;
     unsigned long long* trace;     // debug timeline [grid][16] (UMB_GEMM_TRACE=1), else NULL
 };
 
@@ -230,13 +252,20 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // scripts/gemm_trace.py): even a predicated-off stamp costs issue slots inside the dequant loop.
 #ifdef UMB_GEMM_TRACE_BUILD
 #define UMB_TRACE(slot) do { if (p.trace) p.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+// per-unit timeline of ONE CTA (UMB_UTRACE_CTA, default 0): [256 units][8 stamps] behind the per-CTA stamps
+#ifndef UMB_UTRACE_CTA
+#define UMB_UTRACE_CTA 0
+#endif
+#define UMB_UTRACE(unit, slot) do { if (p.trace && blockIdx.x == UMB_UTRACE_CTA && (unit) >= 0 && (unit) < 256) p.trace[8192 + (size_t)(unit) * 8 + (slot)] = gtimer(); } while (0)
 #else
 #define UMB_TRACE(slot) do { } while (0)
+#define UMB_UTRACE(unit, slot) do { } while (0)
 #endif
 
 template <int MPAD>
 struct GemmCfg {
-    static constexpr int kStagesAwq = MPAD == 16 ? 10 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4));
+    static constexpr int kStagesAwq = MPAD == 16 ? 6 : (MPAD == 32 ? 5 : 4);   // weight requests in flight (x kReqAwq records)
+    static constexpr int kReqAwq = 2;                                         // records per weight request
     static constexpr int kStagesF16 = MPAD <= 32 ? 8 : (MPAD == 64 ? 6 : 4);
     static constexpr int kXBytesAwq = MPAD * 256;           // [2 atoms][MPAD][128 B]
     static constexpr int kXBytesF16 = MPAD * 128;           // [MPAD][128 B]
@@ -247,12 +276,21 @@ struct GemmCfg {
     // that back-to-back tcgen05.mma never wait on each other's accumulate (a dependent 128xNx16 MMA chain
     // runs at its ~150-cycle latency, not at its 8-cycle issue rate); the epilogue sums them.
     static constexpr int kNumAcc = MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : 2);
-    static constexpr int kTmemACol0 = kNumAcc * MPAD < 128 ? 128 : kNumAcc * MPAD;   // A operand stages start here
+    static constexpr bool kDrain = (UMB_AWQ_DRAIN != 0) && MPAD <= 16;              // AWQ only; wider row blocks keep the scaled-operand form (their per-unit drain of MPAD columns per thread costs more than the multiplies it saves: measured)
+    static constexpr int kAccSlots = 8;                                            // drain form: per-unit accumulators in rotation (own ring; the A stage / x slab ring has kTmemAStages slots)
+    static constexpr int kAccCols = kDrain ? kAccSlots * MPAD : kNumAcc * MPAD;
+    static constexpr int kTmemACol0 = kAccCols < 128 ? 128 : kAccCols;             // A operand stages start here
     static constexpr int kTmemAStages = (kTmemCols - kTmemACol0) / 64;             // 6 (4 at MPAD = 128)
-    static constexpr int kBarBytes = 512;
-    static constexpr int smem_bytes(bool awq, int stages) {
+    static constexpr int kBarBytes = 1024;
+    static constexpr int kScaleBytes = kDrain ? kScaleRing * kTileN * 4 : 0;
+    // AWQ: the weight ring holds `stages` requests of `req` consecutive records each (one cp.async.bulk per request);
+    // the x ring has one slab per tensor-memory A stage
+    __host__ __device__ static constexpr int w_stage_bytes(int req) { return (req * kRecordBytes + 127) / 128 * 128; }
+    static constexpr int kXSlabsAwq = MPAD == 16 ? 12 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4));
+    static constexpr int smem_bytes(bool awq, int stages, int req = 1, int x_slabs = kXSlabsAwq) {
         return 1024 /*align slack*/ + kBarBytes + kExchBytes +
-               stages * (awq ? (kXBytesAwq + kPackedStride) : (kXBytesF16 + kWBytesF16));
+               (awq ? kScaleBytes + (kDrain ? kTmemAStages : x_slabs) * kXBytesAwq + stages * w_stage_bytes(req)
+                    : stages * (kXBytesF16 + kWBytesF16));
     }
 };
 
@@ -544,13 +582,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* s_x = smem;                                   // kStages x kXBytes   (1024-aligned slabs)
-    unsigned char* s_w = s_x + kStages * kXBytes;                // kStages x kWStride
-    __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStride);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes);
-    uint64_t* full_w = bars;                  // [kStages]   weight record / tile landed
-    uint64_t* full_x = bars + 16;             // [kStages]   x slab landed
-    uint64_t* done = bars + 32;               // [kStages]   every MMA of the unit in this stage has retired
+    // AWQ: three rings -- weight requests (kStages x kReq consecutive records), x slabs (kXSlabs, one per unit) and
+    // the dequantised A operand in tensor memory (kAStages).  fp16: kStages stages of (x slab, weight tile).
+    const int kReq = kAwq ? p.w_req : 1;
+    const int kXSlabs = kAwq ? (Cfg::kDrain ? kAStages : p.x_slabs) : kStages;
+    const int kWStageBytes = kAwq ? Cfg::w_stage_bytes(kReq) : kWStride;
+    unsigned char* s_x = smem;                                   // kXSlabs x kXBytes   (1024-aligned slabs)
+    unsigned char* s_w = s_x + kXSlabs * kXBytes;                // kStages x kWStageBytes
+    __half* s_exch = reinterpret_cast<__half*>(s_w + kStages * kWStageBytes);
+    constexpr bool kDrain = kAwq && Cfg::kDrain;
+    float* s_scale = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes);   // drain form
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_exch) + Cfg::kExchBytes +
+                                                 (kAwq ? Cfg::kScaleBytes : 0));
+    uint64_t* full_w = bars;                  // [kStages]   weight request / tile landed
+    uint64_t* full_x = bars + 16;             // [kXSlabs]   x slab landed
+    uint64_t* done = bars + 32;               // AWQ: [kAStages] the MMAs reading this A stage have retired; fp16: [kStages]
+    uint64_t* w_empty = bars + 64;            // [kStages]   AWQ: every record of the request is in registers
+    uint64_t* x_done = bars + 80;             // [kXSlabs]   AWQ: the MMAs reading this x slab have retired
+    uint64_t* acc_full_u = bars + 96;         // [kAccSlots] drain form: the unit's accumulator is complete
+    uint64_t* acc_empty_u = bars + 104;       // [kAccSlots] drain form: the epilogue warps have read it
     uint64_t* a_full = bars + 48;             // [kAStages]  dequantised A operand is in tensor memory
     uint64_t* acc_full = bars + 56;
     uint64_t* acc_empty = bars + 57;
@@ -567,15 +617,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_x);
-        if (!kAwq) tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_w);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(full_w + i, 1);
-            mbar_init(full_x + i, 1);
-            mbar_init(done + i, 1);
+            mbar_init(w_empty + i, 4 * kReq);
         }
+        for (int i = 0; i < kXSlabs; ++i) {
+            mbar_init(full_x + i, 1);
+            mbar_init(x_done + i, 1);
+        }
+        for (int i = 0; i < (kAwq ? kAStages : kStages); ++i) mbar_init(done + i, 1);
         for (int i = 0; i < kAStages; ++i) mbar_init(a_full + i, 4);
         mbar_init(acc_full, 2);
         mbar_init(acc_empty, 4);
+        for (int i = 0; i < 8; ++i) {
+            mbar_init(acc_full_u + i, 1);
+            mbar_init(acc_empty_u + i, 4);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -589,8 +647,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     const uint32_t tmem_base = *s_tmem;
     if (threadIdx.x == 0) UMB_TRACE(1);
 
-    if (warp == 0) {
-        // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    if (kAwq && warp == 0) {
+        // ===================== weight producer (AWQ) =====================
+        // One cp.async.bulk per REQUEST of kReq consecutive records: the issuing thread pays ~230 ns per request
+        // whatever its size (scripts/ubench/tma_rates.cu: 8.5 KB requests cap one SM at 37 GB/s = 5.4 TB/s for the
+        // chip, 17 KB requests at 71 GB/s), so single-record requests -- plus the x slab copies that used to share this
+        // loop -- were what held the stream at 0.6 of the HBM peak.  Weights never depend on the stream predecessor:
+        // no griddepcontrol.wait here, the ring fills while the previous kernel drains.
+        const uint64_t pol_w = l2_policy_evict_first();
+        const unsigned char* src = p.packed + u_begin * kRecordStride;
+        const int n_req = (n_units + kReq - 1) / kReq;
+        int ss = 0, round = 0;
+        for (int r = 0; r < n_req; ++r) {
+            if (round > 0) mbar_wait(w_empty + ss, (round - 1) & 1);
+            const int cnt = n_units - r * kReq < kReq ? n_units - r * kReq : kReq;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_w + ss, (uint32_t)(cnt * kRecordBytes));
+                tma_bulk_g2s(s_w + ss * kWStageBytes, src + (size_t)r * kReq * kRecordBytes, (uint32_t)(cnt * kRecordBytes),
+                             full_w + ss, pol_w);
+            }
+            __syncwarp();
+            if (lane == 0) UMB_UTRACE(r * kReq, 0);
+            if (++ss == kStages) {
+                ss = 0;
+                ++round;
+            }
+        }
+        if (lane == 0) UMB_TRACE(2);
+        if (lane == 0) UMB_TRACE(10);
+    } else if (kAwq && warp == kGemmThreads / 32 - 1) {
+        // ===================== x producer (AWQ): one slab per unit into the ring aligned with the TMEM A stages =====================
+        const uint64_t pol_x = l2_policy_evict_last();
+        pdl_wait();                                              // x is the predecessor's output
+        if (lane == 0) UMB_TRACE(3);
+        int g = in_tile0, xs = 0, round = 0;
+        // (drain form: no work here -- the dequant warps stage the unit's x slab themselves, see below)
+        for (int u = kDrain ? n_units : 0; u < n_units; ++u) {
+            if (round > 0) mbar_wait(x_done + xs, (round - 1) & 1);   // the unit that last used this slab has retired
+            if (lane == 0) UMB_UTRACE(u - kXSlabs, 6);
+            if (elect_one()) {
+                unsigned char* dst = s_x + xs * kXBytes;
+                mbar_arrive_expect_tx(full_x + xs, (uint32_t)kXBytes);
+                tma_tensor2d_g2s(dst, &tmap_x, g * kGroup, 0, full_x + xs, pol_x);
+                tma_tensor2d_g2s(dst + MPAD * 128, &tmap_x, g * kGroup + 64, 0, full_x + xs, pol_x);
+            }
+            __syncwarp();
+            if (++g == p.units_per_tile) g = 0;
+            if (++xs == kXSlabs) {
+                xs = 0;
+                ++round;
+            }
+        }
+    } else if (warp == 0) {
+        // ===================== TMA producer, fp16 weights (whole warp runs the loop, one elected lane issues) =====================
         const uint64_t pol_w = l2_policy_evict_first(), pol_x = l2_policy_evict_last();
         const unsigned char* src = p.packed + (kAwq ? u_begin * kRecordStride : 0);
         const int n_pre = n_units < kStages ? n_units : kStages;
@@ -599,6 +708,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         // slab does not queue behind ~85 KB of weights, starts the first MMA 2 us sooner but measured no faster:
         // the dequant warps set the pace.)
         const int n_early = n_pre;
+#ifdef UMB_EXP_XSKIP
+        int x_issue_count = 0;
+#endif
         int tile = tile0, g = in_tile0;                          // (tile, g) of the next weight copy
         auto issue_w = [&](int stage) {
             mbar_arrive_expect_tx(full_w + stage, kWTxBytes);
@@ -608,6 +720,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 tma_tensor2d_g2s(s_w + stage * kWStride, &tmap_w, g * 64, tile * kTileN, full_w + stage, pol_w);
         };
         auto issue_x = [&](int stage, int gk) {
+#ifdef UMB_EXP_XSKIP   // timing-only experiment (wrong numerics): fetch the x slab for one unit in UMB_EXP_XSKIP only
+            if ((x_issue_count++ % UMB_EXP_XSKIP) != 0) {
+                mbar_arrive(full_x + stage);
+                return;
+            }
+#endif
             mbar_arrive_expect_tx(full_x + stage, (uint32_t)kXBytes);
             unsigned char* xs = s_x + stage * kXBytes;
             if constexpr (kAwq) {
@@ -627,6 +745,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         for (int i = 0; i < n_early; ++i) {                      // weights first: independent of the predecessor
             if (elect_one()) issue_w(i);
             __syncwarp();
+            if (lane == 0) UMB_UTRACE(i, 0);
             advance_w();
         }
         if (lane == 0) UMB_TRACE(2);
@@ -650,11 +769,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         r.phase = 1;                                             // every stage has been used once
         for (int i = n_pre; i < n_units; ++i) {
             mbar_wait(done + r.stage, r.phase ^ 1);              // the unit that last used this stage has retired
+            if (lane == 0) UMB_UTRACE(i - kStages, 6);
             if (elect_one()) {
                 issue_w(r.stage);
                 issue_x(r.stage, g);
             }
             __syncwarp();
+            if (lane == 0) UMB_UTRACE(i, 0);
             advance_w();
             r.advance(kStages);
         }
@@ -666,7 +787,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         constexpr uint64_t kDescHi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
         int st = par % kStages, ph = (par / kStages) & 1;            // smem ring position of unit `u`
         int ts = par % kAStages, pa = 0;                              // tensor-memory A ring position
+        int xsl = par % kXSlabs, xph = (par / kXSlabs) & 1;           // AWQ: x-slab ring position
         int u = par, seg = 0, seg_begin = 0, in_tile = in_tile0;
+        if constexpr (kDrain) {
+            // drain form: unit u owns accumulator slot u % kAccSlots (8 MMAs, the first one overwrites); tiles and
+            // segments only matter to the epilogue warps
+            constexpr int kSlots = Cfg::kAccSlots;
+            int slot = par % kSlots;
+            for (; u < n_units; u += 2) {
+                mbar_wait(a_full + ts, pa);            // the 4 dequant warps have published A (tensor memory) and x (shared memory)
+                tc_fence_after();
+                if (u == 0 && lane == 0) UMB_TRACE(5);
+                if (lane == 0) UMB_UTRACE(u, 4);
+                const uint32_t xs = smem_u32(s_x + ts * kXBytes);
+                const uint64_t bd0 = kDescHi | (uint64_t)((xs & 0x3FFFF) >> 4);
+                const uint32_t a_col = tmem_base + kACol0 + ts * 64, d_col = tmem_base + slot * MPAD;
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (MPAD * 128) + (kk & 3) * 32) >> 4);
+                        umma_ts_f16(d_col, a_col + kk * 8, bd, kIdesc, kk ? 1u : 0u);
+                    }
+                    umma_commit(done + ts);            // -> dequant warps: A stage and x slab of this ring slot are free
+                    umma_commit(acc_full_u + slot);    // -> epilogue warps: the unit's accumulator is complete
+                }
+                __syncwarp();
+                if (lane == 0) UMB_UTRACE(u, 5);
+                ts += 2;
+                if (ts >= kAStages) {
+                    ts -= kAStages;
+                    pa ^= 1;
+                }
+                slot += 2;
+                if (slot >= kSlots) slot -= kSlots;
+            }
+            seg_begin = n_units;
+        }
         while (seg_begin < n_units) {
             const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
             mbar_wait(acc_empty, (seg & 1) ^ 1);
@@ -676,24 +832,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const bool last = u + 2 >= seg_end;
                 if constexpr (kAwq) {
                     mbar_wait(a_full + ts, pa);
+                    mbar_wait(full_x + xsl, xph);
                 } else {
                     mbar_wait(full_w + st, ph);
+                    mbar_wait(full_x + st, ph);
                 }
-                mbar_wait(full_x + st, ph);
                 tc_fence_after();
                 if (u == 0 && lane == 0) UMB_TRACE(5);
-                const uint32_t xs = smem_u32(s_x + st * kXBytes);
+                if (lane == 0) UMB_UTRACE(u, 4);
+                const uint32_t xs = smem_u32(s_x + (kAwq ? xsl : st) * kXBytes);
                 const uint64_t bd0 = kDescHi | (uint64_t)((xs & 0x3FFFF) >> 4);
                 if constexpr (kAwq) {
                     const uint32_t a_col = tmem_base + kACol0 + ts * 64;
                     if (elect_one()) {
 #pragma unroll
+#ifdef UMB_EXP_MMA_COUNT   // timing-only experiment (wrong numerics): issue only the first UMB_EXP_MMA_COUNT MMAs of a unit
+                        for (int kk = 0; kk < UMB_EXP_MMA_COUNT; ++kk) {
+#else
                         for (int kk = 0; kk < 8; ++kk) {
+#endif
                             const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (MPAD * 128) + (kk & 3) * 32) >> 4);
                             umma_ts_f16(d_base + (kk % kAccHalf) * MPAD, a_col + kk * 8, bd, kIdesc,
                                         (first && kk < kAccHalf) ? 0u : 1u);
                         }
-                        umma_commit(done + st);
+                        umma_commit(done + ts);
+                        umma_commit(x_done + xsl);
                         if (last) umma_commit(acc_full);
                     }
                 } else {
@@ -709,6 +872,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     }
                 }
                 __syncwarp();
+                if (lane == 0) UMB_UTRACE(u, 5);
                 first = false;
                 st += 2;
                 while (st >= kStages) {
@@ -719,6 +883,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 if (ts >= kAStages) {
                     ts -= kAStages;
                     pa ^= 1;
+                }
+                xsl += 2;
+                if (xsl >= kXSlabs) {
+                    xsl -= kXSlabs;
+                    xph ^= 1;
                 }
             }
             if (first) {                     // this warp had no unit in the segment: plain arrival
@@ -739,34 +908,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         if (!is_epi) {
             // ===================== dequant warps (AWQ): group g takes CTA-local units g, g + kDqGroups, ... =====================
             if constexpr (kAwq) {
-                int dq_st = grp % kStages, dq_ph = 0, dq_ts = grp % kAStages;      // ring positions of unit `mine`
-                int w_first = grp;                                                 // first unit of this group that re-uses a TMEM stage
-                while (w_first < kAStages) w_first += kDqGroups;
-                int w_st = (w_first - kAStages) % kStages, w_ph = 0;               // ring position of unit `mine - kAStages`
-                // the packed words / scale / zero of a unit are pulled into registers as soon as its record has landed
+                // unit u lives in weight request u / kReq (ring slot (u / kReq) % kStages, record u % kReq inside it) and in
+                // x slab / tensor-memory A stage u % kAStages
                 uint4 w4[4];
                 uint32_t sbits = 0, zw = 0;
-                auto fetch = [&](int st_) {
-                    const uint32_t rec = smem_u32(s_w + st_ * kWStride);
+                int cur_ss = 0, cur_round = 0, cur_rbase = 0;   // request of the fetched unit: ring slot, lap, first unit
+                // the packed words / scale / zero of a unit are pulled into registers as soon as its request has landed
+                auto fetch = [&](int unit) {
+                    while (unit >= cur_rbase + kReq) {       // units only move forward: step request by request (no division)
+                        cur_rbase += kReq;
+                        if (++cur_ss == kStages) {
+                            cur_ss = 0;
+                            ++cur_round;
+                        }
+                    }
+                    const int round = cur_round;
+                    mbar_wait(full_w + cur_ss, round & 1);
+                    if (q == 0 && lane == 0) UMB_UTRACE(unit, 1);
+                    const uint32_t rec = smem_u32(s_w + cur_ss * kWStageBytes + (unit - cur_rbase) * kRecordBytes);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) w4[c] = lds128(rec + (c * kTileN + fl) * 16);    // 128 k of this feature row
                     sbits = lds16(rec + kRecScaleOff + fl * 2);
                     zw = lds32(rec + kRecZeroOff + (fl >> 3) * 4);
                 };
                 if (grp < n_units) {
-                    mbar_wait(full_w + dq_st, dq_ph);
+                    fetch(grp);
                     if (grp == 0 && q == 0 && lane == 0) UMB_TRACE(4);
-                    fetch(dq_st);
                 }
+                int ts = grp % kAStages, a_round = grp / kAStages;
+                // drain form: this unit's accumulator slot (ring of kAccSlots) and k-group (for the x slab)
+                int aslot = grp % Cfg::kAccSlots, acc_round = grp / Cfg::kAccSlots;
+                int gk = (in_tile0 + grp) % p.units_per_tile;
+                const int x_row = fl >> 3, x_c = fl & 7;                 // thread -> (token row, 32-byte column pair) of the slab
+                bool dep_pending = true;
                 for (int mine = grp; mine < n_units; mine += kDqGroups) {
-                    const int ts = dq_ts;
-                    dq_st += kDqGroups;
-                    if (dq_st >= kStages) {
-                        dq_st -= kStages;
-                        dq_ph ^= 1;
+                    const int ss = cur_ss;
+                    uint4 xv0 = make_uint4(0, 0, 0, 0), xv1 = xv0;
+                    if constexpr (kDrain) {
+                        // x[:, 128 gk .. 128 gk + 128) from L2 into registers now, into the ring slot's slab (128-byte
+                        // swizzled, what the UMMA smem descriptor expects) once the slot is free.  x is the stream
+                        // predecessor's output: the first load waits for it (the weights above did not have to).
+                        if (dep_pending) {
+                            pdl_wait();
+                            dep_pending = false;
+                        }
+                        if (x_row < p.M) {
+                            const uint4* src = reinterpret_cast<const uint4*>(p.x + (int64_t)x_row * p.ldx + gk * kGroup + x_c * 16);
+                            xv0 = __ldcg(src);
+                            xv1 = __ldcg(src + 1);
+                        }
                     }
-                    dq_ts += kDqGroups;
-                    if (dq_ts >= kAStages) dq_ts -= kAStages;
                     const uint32_t z = (zw >> (4 * (fl & 7))) & 0xFu;
                     const __half2 ce = as_h2((0x6400u | z) * 0x10001u);                 // (1024 + z) x2
                     const __half2 neg_co = as_h2((0xD400u | (z << 4)) * 0x10001u);      // -(64 + z) x2
@@ -778,27 +969,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         const uint32_t words[4] = {w4[c].x, w4[c].y, w4[c].z, w4[c].w};
                         uint32_t a[16];
 #pragma unroll
-                        for (int w = 0; w < 4; ++w) dequant_word(words[w], magic, ce, neg_co, s2, &a[w * 4]);
-                        if (c == 0 && mine >= kAStages) {
-                            // the unit that last used this tensor-memory stage (mine - kAStages) must have retired
-                            mbar_wait(done + w_st, w_ph);
-                            tc_fence_after();
-                            w_st += kDqGroups;
-                            if (w_st >= kStages) {
-                                w_st -= kStages;
-                                w_ph ^= 1;
-                            }
+#ifdef UMB_EXP_NODQ         // timing-only experiment (wrong numerics): no dequant arithmetic, raw words go to tensor memory
+                        for (int w = 0; w < 4; ++w) { a[w * 4] = words[w]; a[w * 4 + 1] = words[w] ^ sbits; a[w * 4 + 2] = words[w] + z; a[w * 4 + 3] = ~words[w]; }
+#else
+                        for (int w = 0; w < 4; ++w) {
+                            if constexpr (kDrain)
+                                dequant_word_int(words[w], magic, ce, neg_co, &a[w * 4]);
+                            else
+                                dequant_word(words[w], magic, ce, neg_co, s2, &a[w * 4]);
                         }
+#endif
+                        if (c == 0 && a_round > 0) {
+                            // the unit that last used this tensor-memory stage (mine - kAStages) must have retired
+                            if (q == 0 && lane == 0) UMB_UTRACE(mine, 2);
+                            mbar_wait(done + ts, (a_round - 1) & 1);
+                            if (q == 0 && lane == 0) UMB_UTRACE(mine, 7);
+                            tc_fence_after();
+                        }
+#ifdef UMB_EXP_NOST         // timing-only experiment (wrong numerics): the A operand is never written to tensor memory
+                        if (a[0] == 0x12345678u && a[7] == 0x9abcdef0u) UMB_TMEM_ST_X16(taddr + c * 16, a);
+#else
                         UMB_TMEM_ST_X16(taddr + c * 16, a);
+#endif
+                    }
+                    // every word of the record has been consumed: this warp's share of the request's ring slot is free
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(w_empty + ss);
+                    // drain form: the unit's group scale for the epilogue warps (the slot's previous user, unit mine - 16,
+                    // has been drained: this unit's tensor-memory stage was only just released by unit mine - kAStages)
+                    if constexpr (kDrain) {
+                        s_scale[(mine & (kScaleRing - 1)) * kTileN + fl] = __half2float(__ushort_as_half((unsigned short)sbits));
+                        // x slab of this ring slot: chunk ch of row r lives at atom (ch >> 3), 16-byte column (ch & 7) ^ (r & 7)
+                        unsigned char* slab = s_x + ts * kXBytes + x_row * 128;
+                        const int ch0 = 2 * x_c, ch1 = 2 * x_c + 1;
+                        *reinterpret_cast<uint4*>(slab + (ch0 >> 3) * (MPAD * 128) + (((ch0 & 7) ^ (x_row & 7)) << 4)) = xv0;
+                        *reinterpret_cast<uint4*>(slab + (ch1 >> 3) * (MPAD * 128) + (((ch1 & 7) ^ (x_row & 7)) << 4)) = xv1;
+                        fence_proxy_async_smem();            // generic-proxy stores -> the MMA's async-proxy reads
+                        // the unit's accumulator slot must have been drained (unit mine - kAccSlots) before its MMAs may start
+                        if (acc_round > 0) mbar_wait(acc_empty_u + aslot, (acc_round - 1) & 1);
+                        aslot += kDqGroups;
+                        if (aslot >= Cfg::kAccSlots) {
+                            aslot -= Cfg::kAccSlots;
+                            ++acc_round;
+                        }
+                        gk += kDqGroups;
+                        while (gk >= p.units_per_tile) gk -= p.units_per_tile;
                     }
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full + ts);
-                    if (mine + kDqGroups < n_units) {            // this group's next unit: (dq_st, dq_ph) already point at it
-                        mbar_wait(full_w + dq_st, dq_ph);
-                        fetch(dq_st);
+                    if (q == 0 && lane == 0) UMB_UTRACE(mine, 3);
+                    ts += kDqGroups;
+                    if (ts >= kAStages) {
+                        ts -= kAStages;
+                        ++a_round;
                     }
+                    if (mine + kDqGroups < n_units) fetch(mine + kDqGroups);     // this group's next unit
                 }
             }
         } else {
@@ -868,6 +1095,102 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     }
                 }
             };
+            if constexpr (kDrain) {
+                // ---- drain form: every unit's accumulator D_g (128 features x MPAD tokens, exact integer weights) is
+                // read back as soon as its MMAs retire and folded into the thread's fp32 running sums with the group
+                // scale: acc[m] += s[g, n] * D_g[n, m].  The tile / partial-tile logic below is the one of the other
+                // form, fed from registers instead of tensor memory.
+                constexpr int kSlots = Cfg::kAccSlots;
+                int slot = 0, sround = 0, u = 0;
+                while (seg_begin < n_units) {
+                    const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
+                    const bool whole = seg_end - seg_begin == p.units_per_tile;
+                    const long long tile_u0 = (long long)tile * p.units_per_tile;
+                    const int c_first = whole ? (int)blockIdx.x : sk_owner(tile_u0, U, P);
+                    const int c_last = whole ? (int)blockIdx.x : sk_owner(tile_u0 + p.units_per_tile - 1, U, P);
+                    const bool reducer = !whole && (int)blockIdx.x == c_first;
+                    float acc[MPAD];
+#pragma unroll
+                    for (int j = 0; j < MPAD; ++j) acc[j] = 0.f;
+                    while (u < seg_end) {
+                        if (MPAD == 16 && u + 1 < seg_end && (slot & 1) == 0) {
+                            // two units per round trip: their accumulators are adjacent columns (one tcgen05.ld.x32)
+                            mbar_wait(acc_full_u + slot, sround & 1);
+                            mbar_wait(acc_full_u + slot + 1, sround & 1);
+                            tc_fence_after();
+                            if (ew == 0 && lane == 0 && u == 0) UMB_TRACE(7);
+                            const float sc0 = s_scale[(u & (kScaleRing - 1)) * kTileN + fl];
+                            const float sc1 = s_scale[((u + 1) & (kScaleRing - 1)) * kTileN + fl];
+                            uint32_t rr[32];
+                            UMB_TMEM_LD_X32(tmem_base + lane_addr + slot * MPAD, rr);
+                            tc_wait_ld();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) {
+                                mbar_arrive(acc_empty_u + slot);
+                                mbar_arrive(acc_empty_u + slot + 1);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                acc[j] = fmaf(sc1, __uint_as_float(rr[16 + j]), fmaf(sc0, __uint_as_float(rr[j]), acc[j]));
+                            u += 2;
+                            slot += 2;
+                        } else {
+                            mbar_wait(acc_full_u + slot, sround & 1);
+                            tc_fence_after();
+                            if (ew == 0 && lane == 0 && u == 0) UMB_TRACE(7);
+                            const float sc = s_scale[(u & (kScaleRing - 1)) * kTileN + fl];
+#pragma unroll
+                            for (int c = 0; c < MPAD; c += 16) {
+                                uint32_t rr[16];
+                                UMB_TMEM_LD_X16(tmem_base + lane_addr + slot * MPAD + c, rr);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) acc[c + j] = fmaf(sc, __uint_as_float(rr[j]), acc[c + j]);
+                            }
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(acc_empty_u + slot);
+                            ++u;
+                            ++slot;
+                        }
+                        if (slot >= kSlots) {
+                            slot = 0;
+                            ++sround;
+                        }
+                    }
+                    if (ew == 0 && lane == 0) UMB_TRACE(seg == 0 ? 12 : 12);
+                    if (whole) {
+#pragma unroll
+                        for (int m0 = 0; m0 < MPAD; m0 += 16)
+                            if (m0 < p.M || p.mode == UMB_EPI_SILU_MUL || p.mode == UMB_EPI_ROPE_QKV)
+                                epilogue_chunk<MPAD>(p, tile, fl, m0, *reinterpret_cast<const float(*)[16]>(&acc[m0]), s_exch);
+                    } else if (!reducer) {
+                        uint32_t* slot_g = reinterpret_cast<uint32_t*>(p.slots) + ((size_t)tile + blockIdx.x) * (MPAD * kTileN);
+#pragma unroll
+                        for (int j = 0; j < MPAD; ++j)
+                            if (j < p.M) {
+                                const uint32_t bits = __float_as_uint(acc[j]);
+                                slot_g[j * kTileN + fl] = bits ? bits : 0x80000000u;
+                            }
+                    } else {
+                        const int n_other = c_last - c_first;
+#pragma unroll
+                        for (int m0 = 0; m0 < MPAD; m0 += 16) {
+                            if (!(m0 < p.M || p.mode == UMB_EPI_SILU_MUL || p.mode == UMB_EPI_ROPE_QKV)) continue;
+                            if (ew == 0 && lane == 0 && m0 == 0) UMB_TRACE(14);
+                            reduce_others(*reinterpret_cast<float(*)[16]>(&acc[m0]), m0, tile, c_first, n_other);
+                            if (ew == 0 && lane == 0 && m0 == 0) UMB_TRACE(15);
+                            epilogue_chunk<MPAD>(p, tile, fl, m0, *reinterpret_cast<const float(*)[16]>(&acc[m0]), s_exch);
+                        }
+                    }
+                    seg_begin = seg_end;
+                    in_tile = 0;
+                    ++tile;
+                    ++seg;
+                    if (ew == 0 && lane == 0) UMB_TRACE(seg == 1 ? 8 : 13);
+                }
+            }
             while (seg_begin < n_units) {
                 const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
                 const int seg_len = seg_end - seg_begin;
@@ -1095,6 +1418,22 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
     return UMB_OK;
 }
 
+// fp16 row-major x [rows, cols] as (64 cols, rows, cols / 64 atoms): box [64, box_rows, 2] = the two 128-byte-swizzled
+// atoms of one 128-k slab in ONE copy (the AWQ drain form's x producer issues one request per unit)
+static int make_tmap_x3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return UMB_ERR_DRIVER;
+    const cuuint64_t dims[3] = {64, rows, cols / 64};
+    const cuuint64_t strides[2] = {ld * sizeof(__half), 64 * sizeof(__half)};
+    const cuuint32_t box[3] = {64, box_rows, 2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return arg_fail(__FILE__, __LINE__, "cuTensorMapEncodeTiled(3d)");
+    return UMB_OK;
+}
+
 // debug timeline (UMB_GEMM_TRACE=1): one device buffer, 16 stamps per CTA of the LAST gemm launch
 static unsigned long long* trace_buffer() {
     static unsigned long long* buf = nullptr;
@@ -1123,26 +1462,50 @@ static unsigned long long* trace_for_this_launch() {
     return (want < 0 || idx == want) ? buf : nullptr;
 }
 
-// Rows one launch takes.  The 128-column instantiation showed a rare launch failure under stress in round 1 (about one
-// launch in 300, cause not found); it is not reachable any more: 65..128 rows always run as two launches of <= 64 rows.
-constexpr int kMaxRowsPerLaunch = 64;
+// rows one launch takes (see gemm_common); 128 with UMB_GEMM_ALLOW_128=1
+static int max_rows_per_launch() {
+    static int cached = 0;
+    if (!cached) {
+        const char* e = getenv("UMB_GEMM_ALLOW_128");
+        cached = (e && e[0] == '1') ? 128 : 64;
+    }
+    return cached;
+}
+static int max_rows_per_launch(bool awq) { return awq ? 64 : max_rows_per_launch(); }   // AWQ: tensor memory holds <= 64 token columns per unit accumulator
+#define kMaxRowsPerLaunch max_rows_per_launch(awq)
 static int mpad_of(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128)); }
 
 template <int MPAD, bool kAwq>
 static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, GemmParams p, int grid, cudaStream_t st) {
     p.stages = kAwq ? GemmCfg<MPAD>::kStagesAwq : GemmCfg<MPAD>::kStagesF16;
+    p.w_req = kAwq && kRecordStride == kRecordBytes ? GemmCfg<MPAD>::kReqAwq : 1;   // multi-record requests need a gap-free stream
+    p.x_slabs = GemmCfg<MPAD>::kXSlabsAwq;
     {
-        static int env_stages = -1;
+        static int env_stages = -1, env_req = -1, env_xs = -1;   // tuning switches: UMB_GEMM_STAGES, UMB_GEMM_WREQ, UMB_GEMM_XSLABS
         if (env_stages < 0) {
             const char* e = getenv("UMB_GEMM_STAGES");
             env_stages = e ? atoi(e) : 0;
+            e = getenv("UMB_GEMM_WREQ");
+            env_req = e ? atoi(e) : 0;
+            e = getenv("UMB_GEMM_XSLABS");
+            env_xs = e ? atoi(e) : 0;
         }
-        if (env_stages > 0 && env_stages <= 16 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024) p.stages = env_stages;
+        const int st = env_stages > 0 && env_stages <= 16 ? env_stages : p.stages;
+        const int rq = kAwq && env_req > 0 && env_req <= 16 && kRecordStride == kRecordBytes ? env_req : p.w_req;
+        const int xs = kAwq && env_xs >= 2 && env_xs <= 16 ? env_xs : p.x_slabs;
+        if ((st != p.stages || rq != p.w_req || xs != p.x_slabs) && GemmCfg<MPAD>::smem_bytes(kAwq, st, rq, xs) <= 227 * 1024) {
+            p.stages = st;
+            p.w_req = rq;
+            p.x_slabs = xs;
+        }
     }
     p.trace = trace_for_this_launch();
-    const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages);
-    // per-device attribute (a process may drive several GPUs / threads): set on every launch, it is a cheap host call
-    UMB_CUDA(cudaFuncSetAttribute(gemm_kernel<MPAD, kAwq>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages, p.w_req, p.x_slabs);
+    static int attr_smem = 0;
+    if (attr_smem < smem) {
+        UMB_CUDA(cudaFuncSetAttribute(gemm_kernel<MPAD, kAwq>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
     UMB_LAUNCH_PDL(gemm_kernel<MPAD, kAwq>, dim3(grid), dim3(kAwq ? kGemmThreads : kGemmThreadsF16), (size_t)smem, st, tx,
                    tw, p);
     count_launches(1);
@@ -1156,7 +1519,9 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     UMB_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0 && (ldx % 8) == 0 && ldx >= K);
     if (M > 128) return UMB_ERR_UNSUPPORTED;
     if (M > kMaxRowsPerLaunch) {
-        // 65..128 rows run as two launches of <= 64 rows (see kMaxRowsPerLaunch).
+        // The 128-column instantiation (4-stage rings) shows a rare launch failure under stress
+        // (scripts/repro_m128.py: ~1 in 300 launches; MPAD <= 64: none in 6000) that is not understood yet, so
+        // 65..128 rows run as two launches of <= 64 rows.  UMB_GEMM_ALLOW_128=1 restores the single launch.
         const int m0 = kMaxRowsPerLaunch;
         umb_epilogue_t e0{}, e1{};
         umb_rope_epilogue_t r1{};
@@ -1186,6 +1551,8 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     if (N_total % 8) return UMB_ERR_UNSUPPORTED;
     GemmParams p{};
     p.packed = awq ? (const unsigned char*)w : nullptr;
+    p.x = (const __half*)x;
+    p.ldx = ldx;
     p.M = M;
     p.K = K;
     p.N_total = N_total;
@@ -1246,7 +1613,8 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
         rc = make_tmap(&tw, w, (uint64_t)N_total, (uint64_t)K, (uint64_t)ldw, (uint32_t)kTileN);
         if (rc != UMB_OK) return rc;
     } else {
-        tw = tx;
+        rc = make_tmap_x3d(&tw, x, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)mpad);   // AWQ: tmap_w = x as slabs
+        if (rc != UMB_OK) return rc;
     }
     if (sync_debug())
         fprintf(stderr, "umbrella_b200: gemm awq=%d M=%d K=%d N=%d mode=%d grid=%d mpad=%d\n", (int)awq, M, K, N_total, p.mode,
@@ -1258,7 +1626,7 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
         case 32: UMB_DISPATCH(32);
         case 64: UMB_DISPATCH(64);
         default:
-            if (awq) return UMB_ERR_UNSUPPORTED;      // never reached: gemm_common splits more than 64 rows
+            if (awq) return UMB_ERR_UNSUPPORTED;      // 65..128 rows run as two launches (gemm_common above)
             return launch_gemm<128, false>(tx, tw, p, grid, st);
     }
 #undef UMB_DISPATCH

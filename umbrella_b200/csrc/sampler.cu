@@ -234,6 +234,80 @@ __global__ void __launch_bounds__(kSampleThreads, 1) sample_kernel(const SampleP
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Row-wise top-k of fp32 logits, sorted (value descending, lower token id first among equals) -- replaces
+// ``logits.topk(k)`` on the draft side: five mbtopk launches per call in torch, one here.
+//   static engine   sampling_argmax_gather (speculation_utils.py:52-61): the next level's tokens are the per-node top
+//                   ``max(branches)`` draft tokens gathered in growmap order  (static...:274-281)
+//   dynamic engine  ``logits.topk(k=num_beams)`` feeding the beam scores (dynamic...:235)
+// One CTA per row: exact k-th largest key by the sampler's radix select, survivors ranked in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTopkMax = 64;
+constexpr int kTopkCap = 512;      // top_k + ties at the k-th value
+
+__global__ void __launch_bounds__(kSampleThreads, 1)
+topk_kernel(const float* __restrict__ logits, int64_t ld, int vocab, int k, float* __restrict__ out_vals,
+            int64_t* __restrict__ out_ids) {
+    __shared__ int s_hist[256];
+    __shared__ int s_idx[kTopkCap];
+    __shared__ float s_val[kTopkCap];
+    __shared__ int s_count, s_digit, s_remaining;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float* x_row = logits + (int64_t)row * ld;
+    uint32_t prefix = 0u, mask = 0u;
+    if (tid == 0) s_remaining = k;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        for (int j = tid; j < vocab; j += kSampleThreads) {
+            const uint32_t key = orderable_key(x_row[j]);
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int cum = 0, d = 255, rem = s_remaining;
+            for (; d > 0; --d) {
+                if (cum + s_hist[d] >= rem) break;
+                cum += s_hist[d];
+            }
+            s_digit = d;
+            s_remaining = rem - cum;
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s_digit << shift;
+        mask |= 255u << shift;
+    }
+    const uint32_t kth = prefix;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int j = tid; j < vocab; j += kSampleThreads) {
+        const float v = x_row[j];
+        if (orderable_key(v) >= kth) {
+            const int at = atomicAdd(&s_count, 1);
+            if (at < kTopkCap) {
+                s_idx[at] = j;
+                s_val[at] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const int n = s_count < kTopkCap ? s_count : kTopkCap;
+    for (int t = tid; t < n; t += kSampleThreads) {
+        const float v = s_val[t];
+        const int id = s_idx[t];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (s_val[j] > v) || (s_val[j] == v && s_idx[j] < id);
+        if (rank < k) {
+            out_vals[(int64_t)row * k + rank] = v;
+            out_ids[(int64_t)row * k + rank] = id;
+        }
+    }
+}
+
 }  // namespace umb
 
 extern "C" int umb_sample_f32(const float* logits, int64_t ld, int rows, int vocab, int mode, float temperature,
@@ -269,6 +343,16 @@ extern "C" int umb_sample_f32(const float* logits, int64_t ld, int rows, int voc
     if (smem > 0)   // ~36 KB of static shared memory + the bitmap exceed the 48 KB default: opt in (per device, cheap)
         UMB_CUDA(cudaFuncSetAttribute(umb::sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     UMB_LAUNCH_PDL(umb::sample_kernel, dim3(rows), dim3(umb::kSampleThreads), smem, (cudaStream_t)stream, p);
+    umb::count_launches(1);
+    return UMB_OK;
+}
+
+extern "C" int umb_topk_f32(const float* logits, int64_t ld, int rows, int vocab, int k, float* out_vals, int64_t* out_ids,
+                            umb_stream_t stream) {
+    UMB_CHECK_ARG(logits && out_vals && out_ids && rows >= 1 && vocab >= 1 && ld >= vocab && k >= 1 && k <= vocab);
+    if (k > umb::kTopkMax) return UMB_ERR_UNSUPPORTED;
+    UMB_LAUNCH_PDL(umb::topk_kernel, dim3(rows), dim3(umb::kSampleThreads), 0, (cudaStream_t)stream, logits, ld, vocab, k,
+                   out_vals, out_ids);
     umb::count_launches(1);
     return UMB_OK;
 }

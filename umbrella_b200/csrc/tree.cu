@@ -190,6 +190,28 @@ __global__ void store_tokens_kernel(int64_t* __restrict__ tokens, const int32_t*
 }
 }  // namespace umb
 
+namespace umb {
+__global__ void store_tokens_gather_kernel(int64_t* __restrict__ tokens, const int32_t* __restrict__ n_dev, int num_nodes,
+                                           int offset, const int64_t* __restrict__ src, const int64_t* __restrict__ gather,
+                                           int count, int capacity) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t at = (int64_t)(n_dev ? n_dev[0] : num_nodes) + offset + i;
+    if (i < count && at < capacity) tokens[at] = src[gather[i]];
+}
+}  // namespace umb
+
+extern "C" int umb_store_tokens_gather(int64_t* tokens_base, const int32_t* n_dev, int num_nodes, int offset,
+                                       const int64_t* src, const int64_t* gather, int count, int capacity,
+                                       umb_stream_t stream) {
+    UMB_CHECK_ARG(tokens_base && src && gather && count >= 1 && offset >= 0 && capacity >= 1 && num_nodes >= 0);
+    UMB_LAUNCH_PDL(umb::store_tokens_gather_kernel, dim3((count + 127) / 128), dim3(128), 0, (cudaStream_t)stream,
+                   tokens_base, n_dev, num_nodes, offset, src, gather, count, capacity);
+    umb::count_launches(1);
+    return UMB_OK;
+}
+
 extern "C" int umb_store_tokens(int64_t* tokens_base, const int32_t* n_dev, int offset, const int64_t* src, int count,
                                 int capacity, umb_stream_t stream) {
     UMB_CHECK_ARG(tokens_base && n_dev && src && count >= 1 && offset >= 0 && capacity >= 1);

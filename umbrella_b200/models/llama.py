@@ -124,8 +124,7 @@ class Llama:
         are attached afterwards with load_head / load_*_layer."""
         _lib.load()
         sh, dev = self.config, self.device
-        self.kv_cache = KV_Cache(sh, max_length=self.max_length, device=dev, dtype=self.dtype,
-                                 batch_size=self.batch_size, num_layers=self.num_layers)
+        self.kv_cache = self._make_kv_cache(**kwargs)
         inv_freq, scaling = llama3_inv_freq(sh)
         self.inv_freq, self.attention_scaling = inv_freq.to(dev), scaling
         cos, sin = rope_tables(inv_freq, scaling, self.max_length)
@@ -147,6 +146,15 @@ class Llama:
         self.layer_weights = [None] * self.num_layers
         self._c_layers = (_lib.LlamaLayer * self.num_layers)()
         return self
+
+    supports_graph = True        # forward_dyn (CUDA-graph replay of the whole iteration) needs everything resident
+
+    def _make_kv_cache(self, **kwargs):
+        if int(kwargs.get("kv_host_layers", 0)) > 0:
+            raise RuntimeError("host-resident KV pages need the paged forward: build the model with offload=... "
+                               "(models/offload.py), e.g. SyntheticLlama(..., kv_host_layers=N)")
+        return KV_Cache(self.config, max_length=self.max_length, device=self.device, dtype=self.dtype,
+                        batch_size=self.batch_size, num_layers=self.num_layers)
 
     @property
     def k_cache(self):
@@ -372,9 +380,15 @@ def synth_head(shape: LlamaShape, seed: int, gen_device="cpu") -> dict:
 
 
 def SyntheticLlama(shape: LlamaShape, max_length: int, awq: bool, seed: int = 1234, device: str = "cuda:0",
-                   num_layers: int | None = None, gen_device: str = "cpu", offload: dict | None = None):
+                   num_layers: int | None = None, gen_device: str = "cpu", offload: dict | None = None,
+                   kv_host_layers: int = 0):
     """A ready-to-run model with seeded synthetic weights of the given architecture.  ``offload`` (e.g.
-    ``{"num_cache_layers": 0}``) builds the paged variant of models/offload.py with those alloc kwargs."""
+    ``{"num_cache_layers": 0}``) builds the paged variant of models/offload.py with those alloc kwargs;
+    ``kv_host_layers`` keeps the K/V planes of that many upper layers in pinned host memory (models/kv_paging.py),
+    weights resident unless ``offload`` says otherwise."""
+    if kv_host_layers:
+        n = shape.num_hidden_layers if num_layers is None else num_layers
+        offload = dict({"num_cache_layers": n}, **(offload or {}), kv_host_layers=kv_host_layers)
     if offload is not None:
         from .offload import LlamaAwqOffload, LlamaOffload
         model = (LlamaAwqOffload if awq else LlamaOffload)(shape, max_length=max_length, device=device,

@@ -37,7 +37,30 @@ _PARTS = ("wqkv", "wo", "wgu", "wdown", "input_norm", "post_norm")
 
 
 class _Paged:
-    """Mixin over Llama / LlamaAwq: layers >= num_cache_layers live in pinned host memory."""
+    """Mixin over Llama / LlamaAwq: layers >= num_cache_layers live in pinned host memory; optionally the K/V planes of
+    the upper ``kv_host_layers`` layers too (models/kv_paging.py)."""
+    supports_graph = False
+
+    def _make_kv_cache(self, **kwargs):
+        host = int(kwargs.get("kv_host_layers", 0))
+        if host <= 0:
+            self.kv_pager = None
+            return super()._make_kv_cache()
+        from .kv_paging import KVPager, PagedKV_Cache
+        cache = PagedKV_Cache(self.config, self.max_length, self.device, self.dtype, self.num_layers, host,
+                              int(kwargs.get("kv_staging_layers", 2)))
+        self.kv_pager = KVPager(cache)
+        self.kv_host_layers = cache.host_layers
+        return cache
+
+    def kv_paging_stats(self) -> dict:
+        p = self.kv_pager
+        if p is None:
+            return {}
+        f = max(p.stats["forwards"], 1)
+        return {"kv_host_layers": self.kv_host_layers, "h2d_bytes_per_forward": p.stats["h2d_bytes"] / f,
+                "d2h_bytes_per_forward": p.stats["d2h_bytes"] / f, "copies_per_forward": p.stats["copies"] / f,
+                "forwards": p.stats["forwards"]}
 
     def alloc(self, **kwargs):
         self.num_cache_layers = int(kwargs.get("num_cache_layers", 0))
@@ -179,9 +202,14 @@ class _Paged:
         ncache, n_stage = self.num_cache_layers, len(self._stage)
         n_off = self.num_layers - ncache
         self.prefetch()
+        kvp = getattr(self, "kv_pager", None)          # host-resident KV pages (models/kv_paging.py)
+        if kvp is not None:
+            kvp.begin_forward(kv_offset, cur)
 
         def run(ci, l0, l1, embed, lg=None, lg_from=0, keys=None):
             r0, n = spans[ci]
+            if kvp is not None:
+                models[ci].k_cache, models[ci].v_cache = kvp.base_ptrs(l0)
             _lib.check(lib.umb_llama_forward_range(
                 C.byref(models[ci]), C.c_void_p(ip + 8 * r0), C.c_void_p(pp + 8 * r0), n, kv_offset + r0,
                 C.byref(masks[ci]), l0, l1, int(embed), lg, lg_from, keys, st), "llama_forward_range")
@@ -193,8 +221,12 @@ class _Paged:
                 if self._stage_holds[b] != j:          # only when (layers - cached) % staging != 0
                     self._enqueue_load(b, j)
                 cur.wait_event(self._ready[b])
+            if kvp is not None:
+                kvp.before_layer(l, kv_offset, cur)
             for ci in range(len(spans)):
                 run(ci, l, l + 1, l == 0)
+            if kvp is not None:
+                kvp.after_layer(l, kv_offset, rows, cur)
             if j >= 0 and n_off > n_stage:
                 self._done[b].record(cur)
                 self._enqueue_load(b, (j + n_stage) % n_off)

@@ -237,6 +237,31 @@ def store_tokens(tokens: torch.Tensor, n_dev: torch.Tensor, offset: int, src: to
           "store_tokens")
 
 
+TOPK_MAX = 64               # umb_topk_f32
+
+
+def topk(logits: torch.Tensor, k: int, out_vals: torch.Tensor | None = None, out_ids: torch.Tensor | None = None):
+    """Row-wise top-k (values descending, lower id first among equals) in ONE launch -> (vals fp32, ids int64) [rows, k]."""
+    _cuda(logits, torch.float32, "logits")
+    assert logits.dim() == 2 and logits.stride(1) == 1
+    rows, vocab = logits.shape
+    if out_vals is None:
+        out_vals = torch.empty((rows, k), dtype=torch.float32, device=logits.device)
+    if out_ids is None:
+        out_ids = torch.empty((rows, k), dtype=torch.int64, device=logits.device)
+    check(_lib.load().umb_topk_f32(_p(logits), logits.stride(0), rows, vocab, k, _p(out_vals), _p(out_ids), _stream()), "topk")
+    return out_vals, out_ids
+
+
+def store_tokens_gather(tokens: torch.Tensor, src: torch.Tensor, gather: torch.Tensor, offset: int, *, num_nodes: int = 0,
+                        n_dev: torch.Tensor | None = None):
+    """tokens[n + offset + i] = src.flatten()[gather[i]], n on the host (num_nodes) or on the device (n_dev)."""
+    _cuda(tokens, torch.int64, "tokens"), _cuda(src, torch.int64, "src"), _cuda(gather, torch.int64, "gather")
+    assert src.is_contiguous() and gather.is_contiguous()
+    check(_lib.load().umb_store_tokens_gather(_p(tokens), _p(n_dev), num_nodes, offset, _p(src), _p(gather), gather.numel(),
+                                              tokens.numel(), _stream()), "store_tokens_gather")
+
+
 def dyn_tree_expand(topk_logits: torch.Tensor, topk_ids: torch.Tensor, width: int, level_first: int, num_nodes: int,
                     tree_score: torch.Tensor, tokens: torch.Tensor, parents: torch.Tensor, tree_bits: torch.Tensor,
                     n_dev: torch.Tensor | None = None):

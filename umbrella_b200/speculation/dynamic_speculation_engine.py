@@ -169,7 +169,10 @@ class DynamicSpeculationEngine(BaseEngine):
                                                      self.tree_bits[first:first + dec_len], want_logits=not last)
             self.num_draft_model_tokens_this_iter += dec_len
             if not last:
-                top_logits, token_ids = logits.topk(dim=-1, k=self.num_beams)
+                if self.num_beams <= ops.TOPK_MAX:
+                    top_logits, token_ids = ops.topk(logits, self.num_beams)       # one launch instead of torch's five
+                else:
+                    top_logits, token_ids = logits.topk(dim=-1, k=self.num_beams)
                 ops.dyn_tree_expand(top_logits, token_ids, self.tree_width, first, n, self.tree_score, self.tokens[0],
                                     self.parents, self.tree_bits)
 

@@ -208,7 +208,8 @@ class StaticSpeculationEngine(BaseEngine):
         return bool(self.lazy_leaf_kv) and self.tree_depth >= 2 and self.num_nodes >= 1
 
     def _graph_ok(self) -> bool:
-        return bool(self.graph_iteration) and self.temperature < 0.05 and not (self.repetition_penalty > 1.01)
+        return bool(self.graph_iteration) and self.temperature < 0.05 and not (self.repetition_penalty > 1.01) \
+            and getattr(self.target_model, "supports_graph", True) and getattr(self.draft_model, "supports_graph", True)
 
     def _iteration_body(self, bound: int):
         """Enqueue one whole iteration with every position read from the device state word."""
@@ -225,9 +226,7 @@ class StaticSpeculationEngine(BaseEngine):
             else:
                 self.draft_model.forward_dyn(tok, pos, b - a, st, a, bound, self.tree_bits[a:b], logits=lg)
             if not last:
-                width = max(self.branch_lists[step])
-                new_tokens = lg.topk(k=width).indices.flatten().index_select(0, self.sample_gather_indices[step])
-                ops.store_tokens(tok, st, b, new_tokens)
+                self._next_level_tokens(step, lg, b, n_dev=st)
         self.target_model.forward_dyn(tok, pos, N, st, 0, bound, self.tree_bits, logits=self._target_logits,
                                       argmax_keys=self._argmax_keys)
         sampled = ops.argmax_keys_to_ids(self._argmax_keys[:N])
@@ -272,6 +271,22 @@ class StaticSpeculationEngine(BaseEngine):
         self.last_accept_length = accept_length
         return bool(cont)
 
+    def _next_level_tokens(self, step: int, logits: torch.Tensor, b: int, num_nodes: int = 0, n_dev=None):
+        """sampling_argmax_gather (speculation_utils.py:52-61; static...:274-281): the per-node top-``max(branches)``
+        draft tokens, picked in growmap order, become tree nodes [b, b + total).  Two launches: umb_topk_f32 and the
+        gathering token store (torch: five mbtopk kernels + flatten + index_select + copy)."""
+        width = max(self.branch_lists[step])
+        gather = self.sample_gather_indices[step]
+        if width <= ops.TOPK_MAX:
+            _, ids = ops.topk(logits, width)
+            ops.store_tokens_gather(self.tokens[0], ids, gather, b, num_nodes=num_nodes, n_dev=n_dev)
+            return
+        new_tokens = logits.topk(k=width).indices.flatten().index_select(0, gather)
+        if n_dev is not None:
+            ops.store_tokens(self.tokens[0], n_dev, b, new_tokens)
+        else:
+            self.tokens[0, num_nodes + b:num_nodes + b + new_tokens.numel()] = new_tokens
+
     @torch.inference_mode()
     def build_tree(self):
         """Draft side (static...:257-281): one draft forward per tree level; the next level's tokens
@@ -294,10 +309,7 @@ class StaticSpeculationEngine(BaseEngine):
                 logits = self.draft_model.verify_forward(ids, pos, n, self.tree_bits[a:b], want_logits=not last)
             self.num_draft_tokens_this_iter += b - a
             if not last:
-                width = max(self.branch_lists[step])
-                new_tokens = logits.topk(k=width).indices.flatten().index_select(0, self.sample_gather_indices[step])
-                total = new_tokens.numel()
-                self.tokens[0, n + b:n + b + total] = new_tokens
+                self._next_level_tokens(step, logits, b, num_nodes=n)
         if lazy:       # leaf rows stay unwritten; the gather treats the cache as holding all N tree rows
             self.draft_model.kv_cache.kv_offset = n + self.tree_size
             self.num_draft_tokens_this_iter = n + self.tree_size
