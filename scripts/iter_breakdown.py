@@ -11,9 +11,10 @@ from umbrella_b200 import ops  # noqa: E402
 from umbrella_b200.speculation.scripted import ScriptedAcceptance  # noqa: E402
 
 dev = "cuda:0"
-eng = bench.build_engine(dev, seed=0)
+WL = bench.WORKLOADS[os.environ.get("WORKLOAD", "static70b")]
+eng = bench.build_engine(dev, WL)
 eng.acceptance_script = ScriptedAcceptance(eng.Successors, seed=1, max_iters=4096, device=dev)
-prompt = torch.randint(3, 30000, (1, bench.PROMPT_LEN), device=dev)
+prompt = torch.randint(3, 30000, (1, WL["prompt"]), device=dev)
 
 
 def ev():

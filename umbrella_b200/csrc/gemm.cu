@@ -49,6 +49,9 @@ constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each,
 constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1);   // producer + 2 MMA issuers + dequant groups + epilogue group (AWQ)
 constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
 constexpr int kTmemCols = 512;
+#ifndef UMB_PAR_ISSUE
+#define UMB_PAR_ISSUE 0                    // ring fill issued by n lanes at once instead of one thread in a loop
+#endif
 // Pipeline variants that were built, measured on B200 and rejected (sleeping mbarrier polls in the idle warps,
 // software-pipelined dequant, x slabs ahead of the weight ring, early residual fetch / early partial-sum
 // reduction, a fourth dequant group) are recorded in profiles/r1_gemm_experiments.txt; none beat this form,
@@ -624,6 +627,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 ++tile;
             }
         };
+#if UMB_PAR_ISSUE
+        // Ring fill: lane i requests stage i, all lanes in the same instruction.  One thread issuing the requests in a
+        // loop pays ~230-350 ns per request (scripts/ubench/tma_rates.cu, tma_issue.cu) -- 3.5 us for a 10-deep ring,
+        // longer than the whole main loop of the small (draft-model, q|k|v, o) GEMMs.
+        {
+            const int gi = in_tile0 + lane;                      // (tile, g) of unit `lane`
+            const int tile_l = tile0 + gi / p.units_per_tile, g_l = gi % p.units_per_tile;
+            if (lane < n_early) {                                // weights first: independent of the predecessor
+                mbar_arrive_expect_tx(full_w + lane, kWTxBytes);
+                if constexpr (kAwq)
+                    tma_bulk_g2s(s_w + lane * kWStride, src + (size_t)lane * kRecordStride, kRecordBytes, full_w + lane, pol_w);
+                else
+                    tma_tensor2d_g2s(s_w + lane * kWStride, &tmap_w, g_l * 64, tile_l * kTileN, full_w + lane, pol_w);
+            }
+            __syncwarp();
+            if (lane == 0) UMB_TRACE(2);
+            pdl_wait();                                          // x is the predecessor's output
+            if (lane == 0) UMB_TRACE(3);
+            if (lane < n_early) issue_x(lane, g_l);
+            __syncwarp();
+            for (int i = 0; i < n_early; ++i) advance_w();
+        }
+#else
         for (int i = 0; i < n_early; ++i) {                      // weights first: independent of the predecessor
             if (elect_one()) issue_w(i);
             __syncwarp();
@@ -638,6 +664,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             __syncwarp();
             if (++gx == p.units_per_tile) gx = 0;
         }
+#endif
         for (int i = n_early; i < n_pre; ++i) {                  // rest of the ring: stages still untouched
             if (elect_one()) {
                 issue_w(i);
