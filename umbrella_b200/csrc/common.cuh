@@ -72,6 +72,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// Same, with a suspend-time hint (ns): the thread stays parked in hardware until the phase completes or the hint
+// expires, instead of coming back to re-issue the poll after the (short) default time limit -- a waiting warp then costs
+// the sub-partition next to no issue slots.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+}
+
 // Ring-buffer cursor: stage index + phase parity.
 struct Ring {
     uint32_t stage = 0, phase = 0;

@@ -45,13 +45,31 @@ constexpr int kRecZeroOff = 8448;
 #ifndef UMB_DQ_GROUPS
 #define UMB_DQ_GROUPS 3
 #endif
-constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each, one per TMEM lane quarter)
-constexpr int kGemmThreads = 96 + 128 * (kDqGroups + 1);   // producer + 2 MMA issuers + dequant groups + epilogue group (AWQ)
-constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights)
-constexpr int kTmemCols = 512;
-#ifndef UMB_PAR_ISSUE
-#define UMB_PAR_ISSUE 0                    // ring fill issued by n lanes at once instead of one thread in a loop
+#ifndef UMB_DQ_GROUPS_16
+#define UMB_DQ_GROUPS_16 UMB_DQ_GROUPS     // dequant groups of the <= 16-row instantiation (the verify pass of the static trees)
 #endif
+constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each, one per TMEM lane quarter)
+constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights); AWQ: GemmCfg::kThreadsAwq
+constexpr int kTmemCols = 512;
+#ifndef UMB_WAIT_HINT
+#define UMB_WAIT_HINT 0                    // 1: mbarrier waits carry a suspend-time hint (short in the pipeline, long in the epilogue)
+#endif
+#if UMB_WAIT_HINT
+#define UMB_WAIT(bar, parity) mbar_wait_hint(bar, parity, 2000u)
+#define UMB_WAIT_LONG(bar, parity) mbar_wait_hint(bar, parity, 100000u)
+#else
+#define UMB_WAIT(bar, parity) mbar_wait(bar, parity)
+#define UMB_WAIT_LONG(bar, parity) mbar_wait(bar, parity)
+#endif
+#ifndef UMB_W_PAIR
+#define UMB_W_PAIR 0                       // 1: the weight producer requests two records per cp.async.bulk (AWQ)
+#endif
+#ifndef UMB_X_PRODUCER
+#define UMB_X_PRODUCER 0                   // 1: the x slabs are requested by their own warp (AWQ), not by the weight producer
+#endif
+#ifndef UMB_AWQ_CTAS
+#define UMB_AWQ_CTAS 1                     // resident AWQ CTAs per SM at <= 32 token rows (2: each CTA takes half of the
+#endif                                     // tensor memory / shared memory and runs 2 dequant groups)
 // Pipeline variants that were built, measured on B200 and rejected (sleeping mbarrier polls in the idle warps,
 // software-pipelined dequant, x slabs ahead of the weight ring, early residual fetch / early partial-sum
 // reduction, a fourth dequant group) are recorded in profiles/r1_gemm_experiments.txt; none beat this form,
@@ -239,7 +257,14 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 template <int MPAD>
 struct GemmCfg {
-    static constexpr int kStagesAwq = MPAD == 16 ? 10 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4));
+    // AWQ kernel only: CTAs resident per SM.  Two half-size CTAs give the SM two TMA-issuing threads, two pairs of MMA
+    // issuers and four dequant groups, and let one CTA's prologue / partial-tile tail overlap the other's main loop.
+    static constexpr int kCtasAwq = (UMB_AWQ_CTAS == 2 && MPAD <= 32) ? 2 : 1;
+    static constexpr int kDq = kCtasAwq == 2 ? 2 : (MPAD == 16 ? UMB_DQ_GROUPS_16 : kDqGroups);                      // dequant groups per CTA (AWQ)
+    static constexpr int kThreadsAwq = 96 + 128 * (kDq + 1) + (UMB_X_PRODUCER ? 32 : 0);
+    static constexpr int kTmem = kTmemCols / kCtasAwq;                             // tensor-memory columns per CTA
+    static constexpr int kStagesAwq = kCtasAwq == 2 ? (MPAD == 16 ? 7 : 5)
+                                                    : (MPAD == 16 ? 10 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4)));
     static constexpr int kStagesF16 = MPAD <= 32 ? 8 : (MPAD == 64 ? 6 : 4);
     static constexpr int kXBytesAwq = MPAD * 256;           // [2 atoms][MPAD][128 B]
     static constexpr int kXBytesF16 = MPAD * 128;           // [MPAD][128 B]
@@ -249,9 +274,9 @@ struct GemmCfg {
     // Independent fp32 accumulators in TMEM (columns a * MPAD): consecutive k-steps rotate through them so
     // that back-to-back tcgen05.mma never wait on each other's accumulate (a dependent 128xNx16 MMA chain
     // runs at its ~150-cycle latency, not at its 8-cycle issue rate); the epilogue sums them.
-    static constexpr int kNumAcc = MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : 2);
-    static constexpr int kTmemACol0 = kNumAcc * MPAD < 128 ? 128 : kNumAcc * MPAD;   // A operand stages start here
-    static constexpr int kTmemAStages = (kTmemCols - kTmemACol0) / 64;             // 6 (4 at MPAD = 128)
+    static constexpr int kNumAcc = kCtasAwq == 2 ? 64 / MPAD : (MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : 2));
+    static constexpr int kTmemACol0 = kCtasAwq == 2 ? 64 : (kNumAcc * MPAD < 128 ? 128 : kNumAcc * MPAD);   // A operand stages start here
+    static constexpr int kTmemAStages = (kTmem - kTmemACol0) / 64;                 // 6 (4 at MPAD = 128; 3 with two CTAs per SM)
     static constexpr int kBarBytes = 512;
     static constexpr int smem_bytes(bool awq, int stages) {
         return 1024 /*align slack*/ + kBarBytes + kExchBytes +
@@ -530,13 +555,15 @@ __device__ __forceinline__ void load_acc_sum(uint32_t taddr, float (&v)[16], int
 //   last 4 warps  epilogue only (AWQ: warps 15..18, fp16: warps 3..6): the partial-tile fix-up is a chain of
 //                 global round trips and must not stall the dequant stream
 template <int MPAD, bool kAwq>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kAwq ? GemmCfg<MPAD>::kThreadsAwq : kGemmThreadsF16, kAwq ? GemmCfg<MPAD>::kCtasAwq : 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
     using Cfg = GemmCfg<MPAD>;
     const int kStages = p.stages;
     constexpr int kXBytes = kAwq ? Cfg::kXBytesAwq : Cfg::kXBytesF16;
-    constexpr int kWStride = kAwq ? Cfg::kPackedStride : Cfg::kWBytesF16;
+    // paired weight requests: two records of the stream land back to back, so the shared-memory stride is the record's
+    constexpr bool kPair = kAwq && UMB_W_PAIR && kRecordStride == kRecordBytes;
+    constexpr int kWStride = kAwq ? (kPair ? kRecordBytes : Cfg::kPackedStride) : Cfg::kWBytesF16;
     constexpr uint32_t kWTxBytes = kAwq ? (uint32_t)kRecordBytes : (uint32_t)Cfg::kWBytesF16;
     constexpr uint32_t kIdesc = umma_idesc_f16(kTileN, MPAD);
     constexpr int kNumAcc = Cfg::kNumAcc;                       // >= 2, even
@@ -544,6 +571,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     constexpr int kAccHalf = kAccUsed / 2;                      // accumulators per MMA warp
     constexpr int kACol0 = Cfg::kTmemACol0;
     constexpr int kAStages = Cfg::kTmemAStages;
+    constexpr int kDq = Cfg::kDq;                               // dequant groups of this CTA
+    constexpr int kTmem = kAwq ? Cfg::kTmem : kTmemCols;
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -582,7 +611,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(s_tmem, kTmemCols);
+        tmem_alloc(s_tmem, kTmem);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -611,6 +640,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 tma_tensor2d_g2s(s_w + stage * kWStride, &tmap_w, g * 64, tile * kTileN, full_w + stage, pol_w);
         };
         auto issue_x = [&](int stage, int gk) {
+            if (kAwq && UMB_X_PRODUCER) return;                   // requested by the x-producer warp
             mbar_arrive_expect_tx(full_x + stage, (uint32_t)kXBytes);
             unsigned char* xs = s_x + stage * kXBytes;
             if constexpr (kAwq) {
@@ -627,29 +657,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 ++tile;
             }
         };
-#if UMB_PAR_ISSUE
-        // Ring fill: lane i requests stage i, all lanes in the same instruction.  One thread issuing the requests in a
-        // loop pays ~230-350 ns per request (scripts/ubench/tma_rates.cu, tma_issue.cu) -- 3.5 us for a 10-deep ring,
-        // longer than the whole main loop of the small (draft-model, q|k|v, o) GEMMs.
-        {
-            const int gi = in_tile0 + lane;                      // (tile, g) of unit `lane`
-            const int tile_l = tile0 + gi / p.units_per_tile, g_l = gi % p.units_per_tile;
-            if (lane < n_early) {                                // weights first: independent of the predecessor
-                mbar_arrive_expect_tx(full_w + lane, kWTxBytes);
-                if constexpr (kAwq)
-                    tma_bulk_g2s(s_w + lane * kWStride, src + (size_t)lane * kRecordStride, kRecordBytes, full_w + lane, pol_w);
-                else
-                    tma_tensor2d_g2s(s_w + lane * kWStride, &tmap_w, g_l * 64, tile_l * kTileN, full_w + lane, pol_w);
+        if constexpr (kPair) {
+            // One request per PAIR of units (17 KB): a thread gets a cp.async.bulk out every ~230 ns whatever its size
+            // (scripts/ubench/tma_rates.cu), so single records cap an SM at 37 GB/s (5.4 TB/s for the chip).  Stages
+            // 2j and 2j + 1 share the barrier full_w[2j]; kStages is even and the ring starts at stage 0, so pairs
+            // never straddle the wrap.
+            auto issue_pair = [&](int stage, int cnt) {
+                mbar_arrive_expect_tx(full_w + stage, (uint32_t)(kRecordBytes * cnt));
+                tma_bulk_g2s(s_w + stage * kWStride, src, (uint32_t)(kRecordBytes * cnt), full_w + stage, pol_w);
+            };
+            for (int i = 0; i < n_pre; i += 2) {                 // weights first: independent of the predecessor
+                const int cnt = n_pre - i >= 2 ? 2 : 1;
+                if (elect_one()) issue_pair(i, cnt);
+                __syncwarp();
+                src += (size_t)kRecordStride * cnt;
             }
-            __syncwarp();
             if (lane == 0) UMB_TRACE(2);
             pdl_wait();                                          // x is the predecessor's output
             if (lane == 0) UMB_TRACE(3);
-            if (lane < n_early) issue_x(lane, g_l);
-            __syncwarp();
-            for (int i = 0; i < n_early; ++i) advance_w();
-        }
-#else
+            int gx = in_tile0;
+            for (int i = 0; i < n_pre; ++i) {
+                if (elect_one()) issue_x(i, gx);
+                __syncwarp();
+                if (++gx == p.units_per_tile) gx = 0;
+            }
+            int stage = 0, use = 1;
+            for (int i = n_pre; i < n_units; i += 2) {
+                const int cnt = n_units - i >= 2 ? 2 : 1;
+                UMB_WAIT(done + stage, (use - 1) & 1);          // the units that last used these stages have retired
+                if (cnt == 2) UMB_WAIT(done + stage + 1, (use - 1) & 1);
+                if (elect_one()) {
+                    issue_pair(stage, cnt);
+                    issue_x(stage, gx);
+                    if (cnt == 2) issue_x(stage + 1, gx + 1 == p.units_per_tile ? 0 : gx + 1);
+                }
+                __syncwarp();
+                src += (size_t)kRecordStride * cnt;
+                for (int c = 0; c < cnt; ++c)
+                    if (++gx == p.units_per_tile) gx = 0;
+                stage += 2;
+                if (stage >= kStages) {
+                    stage = 0;
+                    ++use;
+                }
+            }
+        } else {
         for (int i = 0; i < n_early; ++i) {                      // weights first: independent of the predecessor
             if (elect_one()) issue_w(i);
             __syncwarp();
@@ -664,7 +716,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             __syncwarp();
             if (++gx == p.units_per_tile) gx = 0;
         }
-#endif
         for (int i = n_early; i < n_pre; ++i) {                  // rest of the ring: stages still untouched
             if (elect_one()) {
                 issue_w(i);
@@ -676,7 +727,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         Ring r;
         r.phase = 1;                                             // every stage has been used once
         for (int i = n_pre; i < n_units; ++i) {
-            mbar_wait(done + r.stage, r.phase ^ 1);              // the unit that last used this stage has retired
+            UMB_WAIT(done + r.stage, r.phase ^ 1);              // the unit that last used this stage has retired
             if (elect_one()) {
                 issue_w(r.stage);
                 issue_x(r.stage, g);
@@ -685,7 +736,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             advance_w();
             r.advance(kStages);
         }
+        }
         if (lane == 0) UMB_TRACE(10);
+    } else if (kAwq && UMB_X_PRODUCER && warp == GemmCfg<MPAD>::kThreadsAwq / 32 - 1) {
+        // ===================== x-slab producer (AWQ, UMB_X_PRODUCER): two tensor copies per unit =====================
+        const uint64_t pol_x = l2_policy_evict_last();
+        pdl_wait();                                              // x is the predecessor's output
+        int gx = in_tile0, stage = 0, use = 0;
+        for (int i = 0; i < n_units; ++i) {
+            if (use > 0) UMB_WAIT(done + stage, (use - 1) & 1); // the unit that last used this stage has retired
+            if (elect_one()) {
+                mbar_arrive_expect_tx(full_x + stage, (uint32_t)kXBytes);
+                unsigned char* xs = s_x + stage * kXBytes;
+                tma_tensor2d_g2s(xs, &tmap_x, gx * kGroup, 0, full_x + stage, pol_x);
+                tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, gx * kGroup + 64, 0, full_x + stage, pol_x);
+            }
+            __syncwarp();
+            if (++gx == p.units_per_tile) gx = 0;
+            if (++stage == kStages) {
+                stage = 0;
+                ++use;
+            }
+        }
     } else if (warp <= 2) {
         // ===================== MMA issuers: warp 1 takes even CTA-local units, warp 2 odd ones =====================
         const int par = warp - 1;
@@ -696,17 +768,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         int u = par, seg = 0, seg_begin = 0, in_tile = in_tile0;
         while (seg_begin < n_units) {
             const int seg_end = seg_begin + min(n_units - seg_begin, p.units_per_tile - in_tile);
-            mbar_wait(acc_empty, (seg & 1) ^ 1);
+            UMB_WAIT_LONG(acc_empty, (seg & 1) ^ 1);
             tc_fence_after();
             bool first = true;
             for (; u < seg_end; u += 2) {
                 const bool last = u + 2 >= seg_end;
                 if constexpr (kAwq) {
-                    mbar_wait(a_full + ts, pa);
+                    UMB_WAIT(a_full + ts, pa);
                 } else {
-                    mbar_wait(full_w + st, ph);
+                    UMB_WAIT(full_w + st, ph);
                 }
-                mbar_wait(full_x + st, ph);
+                UMB_WAIT(full_x + st, ph);
                 tc_fence_after();
                 if (u == 0 && lane == 0) UMB_TRACE(5);
                 const uint32_t xs = smem_u32(s_x + st * kXBytes);
@@ -760,7 +832,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     } else {
         const int q = warp & 3;                      // TMEM lane quarter this warp may touch
         const int grp = (warp - 3) >> 2;             // AWQ: dequant group 0..kDqGroups-1, then the epilogue group
-        const bool is_epi = kAwq ? (grp == kDqGroups) : true;
+        const bool is_epi = kAwq ? (grp == kDq) : true;
         const int fl = q * 32 + lane;                // feature lane 0..127
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         if (!is_epi) {
@@ -768,7 +840,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             if constexpr (kAwq) {
                 int dq_st = grp % kStages, dq_ph = 0, dq_ts = grp % kAStages;      // ring positions of unit `mine`
                 int w_first = grp;                                                 // first unit of this group that re-uses a TMEM stage
-                while (w_first < kAStages) w_first += kDqGroups;
+                while (w_first < kAStages) w_first += kDq;
                 int w_st = (w_first - kAStages) % kStages, w_ph = 0;               // ring position of unit `mine - kAStages`
                 // the packed words / scale / zero of a unit are pulled into registers as soon as its record has landed
                 uint4 w4[4];
@@ -781,18 +853,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     zw = lds32(rec + kRecZeroOff + (fl >> 3) * 4);
                 };
                 if (grp < n_units) {
-                    mbar_wait(full_w + dq_st, dq_ph);
+                    UMB_WAIT(full_w + (kPair ? (dq_st & ~1) : dq_st), dq_ph);
                     if (grp == 0 && q == 0 && lane == 0) UMB_TRACE(4);
                     fetch(dq_st);
                 }
-                for (int mine = grp; mine < n_units; mine += kDqGroups) {
+                for (int mine = grp; mine < n_units; mine += kDq) {
                     const int ts = dq_ts;
-                    dq_st += kDqGroups;
+                    dq_st += kDq;
                     if (dq_st >= kStages) {
                         dq_st -= kStages;
                         dq_ph ^= 1;
                     }
-                    dq_ts += kDqGroups;
+                    dq_ts += kDq;
                     if (dq_ts >= kAStages) dq_ts -= kAStages;
                     const uint32_t z = (zw >> (4 * (fl & 7))) & 0xFu;
                     const __half2 ce = as_h2((0x6400u | z) * 0x10001u);                 // (1024 + z) x2
@@ -808,9 +880,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         for (int w = 0; w < 4; ++w) dequant_word(words[w], magic, ce, neg_co, s2, &a[w * 4]);
                         if (c == 0 && mine >= kAStages) {
                             // the unit that last used this tensor-memory stage (mine - kAStages) must have retired
-                            mbar_wait(done + w_st, w_ph);
+                            UMB_WAIT(done + w_st, w_ph);
                             tc_fence_after();
-                            w_st += kDqGroups;
+                            w_st += kDq;
                             if (w_st >= kStages) {
                                 w_st -= kStages;
                                 w_ph ^= 1;
@@ -822,15 +894,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full + ts);
-                    if (mine + kDqGroups < n_units) {            // this group's next unit: (dq_st, dq_ph) already point at it
-                        mbar_wait(full_w + dq_st, dq_ph);
+                    if (mine + kDq < n_units) {            // this group's next unit: (dq_st, dq_ph) already point at it
+                        UMB_WAIT(full_w + (kPair ? (dq_st & ~1) : dq_st), dq_ph);
                         fetch(dq_st);
                     }
                 }
             }
         } else {
             // ===================== epilogue warps =====================
-            const int ew = kAwq ? warp - 3 - 4 * kDqGroups : warp - 3;       // 0..3 inside the epilogue group
+            const int ew = kAwq ? warp - 3 - 4 * kDq : warp - 3;       // 0..3 inside the epilogue group
             pdl_wait();                                  // residual / workspace / y belong to the predecessors
             if (ew == 0 && lane == 0) UMB_TRACE(11);
             int seg = 0, seg_begin = 0, in_tile = in_tile0, tile = tile0;
@@ -906,7 +978,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const int c_first = whole ? (int)blockIdx.x : sk_owner(tile_u0, U, P);
                 const int c_last = whole ? (int)blockIdx.x : sk_owner(tile_u0 + p.units_per_tile - 1, U, P);
                 const bool reducer = !whole && (int)blockIdx.x == c_first;
-                mbar_wait(acc_full, seg & 1);
+                UMB_WAIT_LONG(acc_full, seg & 1);
                 tc_fence_after();
                 if (ew == 0 && lane == 0) UMB_TRACE(seg == 0 ? 7 : 12);
                 if (whole) {
@@ -981,7 +1053,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     if (threadIdx.x == 0) UMB_TRACE(9);
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, kTmem);
     }
 }
 
@@ -1164,13 +1236,14 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, GemmParams 
             const char* e = getenv("UMB_GEMM_STAGES");
             env_stages = e ? atoi(e) : 0;
         }
-        if (env_stages > 0 && env_stages <= 16 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024) p.stages = env_stages;
+        if (env_stages > 0 && env_stages <= 16 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024 / (kAwq ? GemmCfg<MPAD>::kCtasAwq : 1) - 1024)
+            p.stages = env_stages;
     }
     p.trace = trace_for_this_launch();
     const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages);
     // per-device attribute (a process may drive several GPUs / threads): set on every launch, it is a cheap host call
     UMB_CUDA(cudaFuncSetAttribute(gemm_kernel<MPAD, kAwq>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    UMB_LAUNCH_PDL(gemm_kernel<MPAD, kAwq>, dim3(grid), dim3(kAwq ? kGemmThreads : kGemmThreadsF16), (size_t)smem, st, tx,
+    UMB_LAUNCH_PDL(gemm_kernel<MPAD, kAwq>, dim3(grid), dim3(kAwq ? GemmCfg<MPAD>::kThreadsAwq : kGemmThreadsF16), (size_t)smem, st, tx,
                    tw, p);
     count_launches(1);
     return UMB_OK;
@@ -1245,7 +1318,7 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     const int mpad = mpad_of(M);
     const long long U = (long long)p.tiles * p.units_per_tile;
     if (U >= (1ll << 31)) return UMB_ERR_UNSUPPORTED;
-    int grid = sm_count();
+    int grid = sm_count() * ((awq && mpad <= 32) ? UMB_AWQ_CTAS : 1);
     if ((long long)grid > U) grid = (int)U;
     static int aligned_split = -1;                   // UMB_GEMM_ALIGNED_SPLIT=0: plain stream-K for small problems too (tuning)
     if (aligned_split < 0) {
