@@ -52,7 +52,7 @@ constexpr int kDqGroups = UMB_DQ_GROUPS;   // dequant warp groups (4 warps each,
 constexpr int kGemmThreadsF16 = 96 + 128;           // producer + 2 MMA issuers + 4 epilogue warps (fp16 weights); AWQ: GemmCfg::kThreadsAwq
 constexpr int kTmemCols = 512;
 #ifndef UMB_WAIT_HINT
-#define UMB_WAIT_HINT 0                    // 1: mbarrier waits carry a suspend-time hint (short in the pipeline, long in the epilogue)
+#define UMB_WAIT_HINT 1                    // 1: mbarrier waits carry a suspend-time hint (short in the pipeline, long in the epilogue)
 #endif
 #if UMB_WAIT_HINT
 #define UMB_WAIT(bar, parity) mbar_wait_hint(bar, parity, 2000u)
@@ -60,6 +60,9 @@ constexpr int kTmemCols = 512;
 #else
 #define UMB_WAIT(bar, parity) mbar_wait(bar, parity)
 #define UMB_WAIT_LONG(bar, parity) mbar_wait(bar, parity)
+#endif
+#ifndef UMB_X_3D
+#define UMB_X_3D 1                         // 1: one 3-D tensor copy per x slab (both 64-k atoms) instead of two 2-D copies (AWQ)
 #endif
 #ifndef UMB_W_PAIR
 #define UMB_W_PAIR 0                       // 1: the weight producer requests two records per cp.async.bulk (AWQ)
@@ -599,7 +602,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_x);
-        if (!kAwq) tma_prefetch_desc(&tmap_w);
+        if (!kAwq || UMB_X_3D) tma_prefetch_desc(&tmap_w);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(full_w + i, 1);
             mbar_init(full_x + i, 1);
@@ -643,7 +646,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             if (kAwq && UMB_X_PRODUCER) return;                   // requested by the x-producer warp
             mbar_arrive_expect_tx(full_x + stage, (uint32_t)kXBytes);
             unsigned char* xs = s_x + stage * kXBytes;
-            if constexpr (kAwq) {
+            if constexpr (kAwq && UMB_X_3D) {
+                tma_tensor3d_g2s(xs, &tmap_w, 0, 0, gk * 2, full_x + stage, pol_x);      // tmap_w = x as [64, rows, K / 64]
+            } else if constexpr (kAwq) {
                 tma_tensor2d_g2s(xs, &tmap_x, gk * kGroup, 0, full_x + stage, pol_x);
                 tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, gk * kGroup + 64, 0, full_x + stage, pol_x);
             } else {
@@ -748,8 +753,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             if (elect_one()) {
                 mbar_arrive_expect_tx(full_x + stage, (uint32_t)kXBytes);
                 unsigned char* xs = s_x + stage * kXBytes;
-                tma_tensor2d_g2s(xs, &tmap_x, gx * kGroup, 0, full_x + stage, pol_x);
-                tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, gx * kGroup + 64, 0, full_x + stage, pol_x);
+                if constexpr (UMB_X_3D) {
+                    tma_tensor3d_g2s(xs, &tmap_w, 0, 0, gx * 2, full_x + stage, pol_x);
+                } else {
+                    tma_tensor2d_g2s(xs, &tmap_x, gx * kGroup, 0, full_x + stage, pol_x);
+                    tma_tensor2d_g2s(xs + MPAD * 128, &tmap_x, gx * kGroup + 64, 0, full_x + stage, pol_x);
+                }
             }
             __syncwarp();
             if (++gx == p.units_per_tile) gx = 0;
@@ -1194,6 +1203,22 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
     return UMB_OK;
 }
 
+// fp16 row-major x [rows, cols] as (64 cols, rows, cols / 64 atoms): box [64, box_rows, 2] = the two 128-byte-swizzled
+// atoms of one 128-k slab in ONE copy
+static int make_tmap_x3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return UMB_ERR_DRIVER;
+    const cuuint64_t dims[3] = {64, rows, cols / 64};
+    const cuuint64_t strides[2] = {ld * sizeof(__half), 64 * sizeof(__half)};
+    const cuuint32_t box[3] = {64, box_rows, 2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return arg_fail(__FILE__, __LINE__, "cuTensorMapEncodeTiled(3d)");
+    return UMB_OK;
+}
+
 // debug timeline (UMB_GEMM_TRACE=1): one device buffer, 16 stamps per CTA of the LAST gemm launch
 static unsigned long long* trace_buffer() {
     static unsigned long long* buf = nullptr;
@@ -1224,7 +1249,10 @@ static unsigned long long* trace_for_this_launch() {
 
 // Rows one launch takes.  The 128-column instantiation showed a rare launch failure under stress in round 1 (about one
 // launch in 300, cause not found); it is not reachable any more: 65..128 rows always run as two launches of <= 64 rows.
-constexpr int kMaxRowsPerLaunch = 64;
+#ifndef UMB_MAX_ROWS
+#define UMB_MAX_ROWS 64                    // 128: debugging build that launches the 128-column AWQ instantiation directly
+#endif
+constexpr int kMaxRowsPerLaunch = UMB_MAX_ROWS;
 static int mpad_of(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128)); }
 
 template <int MPAD, bool kAwq>
@@ -1345,6 +1373,9 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
         UMB_CHECK_ARG((ldw % 8) == 0 && ldw >= K);
         rc = make_tmap(&tw, w, (uint64_t)N_total, (uint64_t)K, (uint64_t)ldw, (uint32_t)kTileN);
         if (rc != UMB_OK) return rc;
+    } else if (UMB_X_3D) {
+        rc = make_tmap_x3d(&tw, x, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, (uint32_t)mpad);   // AWQ: tmap_w = x as slabs
+        if (rc != UMB_OK) return rc;
     } else {
         tw = tx;
     }
@@ -1358,8 +1389,12 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
         case 32: UMB_DISPATCH(32);
         case 64: UMB_DISPATCH(64);
         default:
+#if UMB_MAX_ROWS > 64
+            UMB_DISPATCH(128);
+#else
             if (awq) return UMB_ERR_UNSUPPORTED;      // never reached: gemm_common splits more than 64 rows
             return launch_gemm<128, false>(tx, tw, p, grid, st);
+#endif
     }
 #undef UMB_DISPATCH
 }
