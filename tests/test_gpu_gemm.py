@@ -212,9 +212,11 @@ def test_fused_rope_qkv_epilogue_is_bit_identical(awq, M, Hq, Hkv, D, K):
 
 @pytest.mark.parametrize("M", [65, 97, 128])
 def test_rows_above_64_are_stable_and_correct(M):
-    """Regression for the rare launch failure of the 128-column GEMM instantiation (scripts/repro_m128.py): calls
-    with 65..128 rows run as two launches of <= 64 rows; 200 back-to-back launches at a 70B q|k|v shape must all
-    succeed, leave the workspace clean and agree with the first result bit for bit (deterministic reduction)."""
+    """Regression for the rare launch failure of the 128-column GEMM instantiation (scripts/repro_m128.py; root cause:
+    a parity wait two phases ahead of its barrier in the 4-deep ring, profiles/r2_m128_root_cause.txt -- 24 000 launches
+    clean after the fix, one in ~150 failing before): 200 back-to-back single launches of 65..128 rows at a 70B q|k|v
+    shape must all succeed, leave the workspace clean and agree with the first result bit for bit (deterministic
+    reduction)."""
     from umbrella_b200 import ops
     K, N = 8192, 10240
     rng = np.random.default_rng(M)

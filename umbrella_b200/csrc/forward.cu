@@ -18,7 +18,7 @@ static int linear(const umb_llama_t* m, const void* x, int64_t ldx, const void* 
 
 #define UMB_TRY(expr) do { int rc__ = (expr); if (rc__ != UMB_OK) return rc__; } while (0)
 
-constexpr int kChunkRows = 64;
+constexpr int kChunkRows = UMB_MAX_ROWS;
 
 // UMB_FUSE_ROPE=1 runs the q|k|v projection with the fused RoPE + KV-append epilogue (UMB_EPI_ROPE_QKV) instead of
 // the GEMM + rope_append kernel pair.  Off by default: bit-identical, one launch fewer, but measured slower
@@ -137,9 +137,8 @@ extern "C" int umb_llama_forward(const umb_llama_t* m, const int64_t* input_ids,
     UMB_CHECK_ARG(kv_offset + rows <= m->max_length);
     UMB_CHECK_ARG(!argmax_keys || logits);
     if (logits) UMB_CHECK_ARG(m->lm_head != nullptr);
-    // rows > 64 (prefill, dynamic trees of 257..505 nodes): equal chunks of <= 64 rows, each a full pass
-    // over the weights; later chunks see the KV rows the earlier ones appended.  (64, not 128: the GEMM's
-    // 128-column instantiation is held back, see gemm_common.)
+    // rows > 128 (prefill, dynamic trees of 257..505 nodes): equal chunks of <= 128 rows, each a full pass
+    // over the weights; later chunks see the KV rows the earlier ones appended.
     const int n_chunks = (rows + umb::kChunkRows - 1) / umb::kChunkRows;
     const int chunk = (rows + n_chunks - 1) / n_chunks;
     for (int r0 = 0; r0 < rows; r0 += chunk) {

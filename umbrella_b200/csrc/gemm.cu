@@ -70,9 +70,6 @@ constexpr int kTmemCols = 512;
 #ifndef UMB_X_PRODUCER
 #define UMB_X_PRODUCER 0                   // 1: the x slabs are requested by their own warp (AWQ), not by the weight producer
 #endif
-#ifndef UMB_AWQ_CTAS
-#define UMB_AWQ_CTAS 1                     // resident AWQ CTAs per SM at <= 32 token rows (2: each CTA takes half of the
-#endif                                     // tensor memory / shared memory and runs 2 dequant groups)
 // Pipeline variants that were built, measured on B200 and rejected (sleeping mbarrier polls in the idle warps,
 // software-pipelined dequant, x slabs ahead of the weight ring, early residual fetch / early partial-sum
 // reduction, a fourth dequant group) are recorded in profiles/r1_gemm_experiments.txt; none beat this form,
@@ -260,14 +257,9 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 template <int MPAD>
 struct GemmCfg {
-    // AWQ kernel only: CTAs resident per SM.  Two half-size CTAs give the SM two TMA-issuing threads, two pairs of MMA
-    // issuers and four dequant groups, and let one CTA's prologue / partial-tile tail overlap the other's main loop.
-    static constexpr int kCtasAwq = (UMB_AWQ_CTAS == 2 && MPAD <= 32) ? 2 : 1;
-    static constexpr int kDq = kCtasAwq == 2 ? 2 : (MPAD == 16 ? UMB_DQ_GROUPS_16 : kDqGroups);                      // dequant groups per CTA (AWQ)
+    static constexpr int kDq = MPAD == 16 ? UMB_DQ_GROUPS_16 : kDqGroups;           // dequant groups per CTA (AWQ)
     static constexpr int kThreadsAwq = 96 + 128 * (kDq + 1) + (UMB_X_PRODUCER ? 32 : 0);
-    static constexpr int kTmem = kTmemCols / kCtasAwq;                             // tensor-memory columns per CTA
-    static constexpr int kStagesAwq = kCtasAwq == 2 ? (MPAD == 16 ? 7 : 5)
-                                                    : (MPAD == 16 ? 10 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4)));
+    static constexpr int kStagesAwq = MPAD == 16 ? 10 : (MPAD == 32 ? 8 : (MPAD == 64 ? 6 : 4));
     static constexpr int kStagesF16 = MPAD <= 32 ? 8 : (MPAD == 64 ? 6 : 4);
     static constexpr int kXBytesAwq = MPAD * 256;           // [2 atoms][MPAD][128 B]
     static constexpr int kXBytesF16 = MPAD * 128;           // [MPAD][128 B]
@@ -277,9 +269,9 @@ struct GemmCfg {
     // Independent fp32 accumulators in TMEM (columns a * MPAD): consecutive k-steps rotate through them so
     // that back-to-back tcgen05.mma never wait on each other's accumulate (a dependent 128xNx16 MMA chain
     // runs at its ~150-cycle latency, not at its 8-cycle issue rate); the epilogue sums them.
-    static constexpr int kNumAcc = kCtasAwq == 2 ? 64 / MPAD : (MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : 2));
-    static constexpr int kTmemACol0 = kCtasAwq == 2 ? 64 : (kNumAcc * MPAD < 128 ? 128 : kNumAcc * MPAD);   // A operand stages start here
-    static constexpr int kTmemAStages = (kTmem - kTmemACol0) / 64;                 // 6 (4 at MPAD = 128; 3 with two CTAs per SM)
+    static constexpr int kNumAcc = MPAD <= 16 ? 8 : (MPAD == 32 ? 4 : 2);
+    static constexpr int kTmemACol0 = kNumAcc * MPAD < 128 ? 128 : kNumAcc * MPAD;   // A operand stages start here
+    static constexpr int kTmemAStages = (kTmemCols - kTmemACol0) / 64;             // 6 (4 at MPAD = 128)
     static constexpr int kBarBytes = 512;
     static constexpr int smem_bytes(bool awq, int stages) {
         return 1024 /*align slack*/ + kBarBytes + kExchBytes +
@@ -558,7 +550,7 @@ __device__ __forceinline__ void load_acc_sum(uint32_t taddr, float (&v)[16], int
 //   last 4 warps  epilogue only (AWQ: warps 15..18, fp16: warps 3..6): the partial-tile fix-up is a chain of
 //                 global round trips and must not stall the dequant stream
 template <int MPAD, bool kAwq>
-__global__ void __launch_bounds__(kAwq ? GemmCfg<MPAD>::kThreadsAwq : kGemmThreadsF16, kAwq ? GemmCfg<MPAD>::kCtasAwq : 1)
+__global__ void __launch_bounds__(kAwq ? GemmCfg<MPAD>::kThreadsAwq : kGemmThreadsF16, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
     using Cfg = GemmCfg<MPAD>;
@@ -574,8 +566,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     constexpr int kAccHalf = kAccUsed / 2;                      // accumulators per MMA warp
     constexpr int kACol0 = Cfg::kTmemACol0;
     constexpr int kAStages = Cfg::kTmemAStages;
+    // the MMA warps take alternate units, so a ring stage must always come back to the same warp (parity waits, see the
+    // dequant warps' note): both rings need an even depth
+    static_assert(!kAwq || (kAStages % 2 == 0 && Cfg::kStagesAwq % 2 == 0), "ring depths must be even");
     constexpr int kDq = Cfg::kDq;                               // dequant groups of this CTA
-    constexpr int kTmem = kAwq ? Cfg::kTmem : kTmemCols;
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -614,7 +608,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(s_tmem, kTmem);
+        tmem_alloc(s_tmem, kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -904,6 +898,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full + ts);
                     if (mine + kDq < n_units) {            // this group's next unit: (dq_st, dq_ph) already point at it
+                        // A parity wait is only sound if the waiter cannot be TWO phases ahead of the barrier: waiting for
+                        // use j of a stage while use j - 1 is still in flight passes at once (the parity of "j - 2
+                        // completed" equals that of "j completed").  The previous occupant of this stage is unit
+                        // mine + kDq - kStages, which belongs to another group and may not even have landed yet when the
+                        // ring is as short as 4 stages (the 128-column instantiation: unit mine - 1) -- the group then read a
+                        // stale record, signalled a_full early, and the producer re-armed a barrier whose phase was still
+                        // open: the "Warp Illegal Instruction" (mbarrier arrive on an exhausted phase) that killed about
+                        // one 128-row launch in 150 (profiles/r2_m128_root_cause.txt).  Waiting for the previous occupant to
+                        // have RETIRED first closes it: the producer has waited for every done[] up to unit mine - kStages
+                        // in order before it issued `mine`, so this done[] wait can be at most one phase ahead, and once it
+                        // passes, full_w is at most one phase behind.
+                        if (mine + kDq >= kStages) UMB_WAIT(done + dq_st, dq_ph ^ 1);
                         UMB_WAIT(full_w + (kPair ? (dq_st & ~1) : dq_st), dq_ph);
                         fetch(dq_st);
                     }
@@ -1062,7 +1068,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     if (threadIdx.x == 0) UMB_TRACE(9);
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmem);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -1247,11 +1253,7 @@ static unsigned long long* trace_for_this_launch() {
     return (want < 0 || idx == want) ? buf : nullptr;
 }
 
-// Rows one launch takes.  The 128-column instantiation showed a rare launch failure under stress in round 1 (about one
-// launch in 300, cause not found); it is not reachable any more: 65..128 rows always run as two launches of <= 64 rows.
-#ifndef UMB_MAX_ROWS
-#define UMB_MAX_ROWS 64                    // 128: debugging build that launches the 128-column AWQ instantiation directly
-#endif
+// Rows one launch takes (internal.h: UMB_MAX_ROWS; 64 splits 65..128 rows into two launches as round 1 did).
 constexpr int kMaxRowsPerLaunch = UMB_MAX_ROWS;
 static int mpad_of(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128)); }
 
@@ -1264,8 +1266,8 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, GemmParams 
             const char* e = getenv("UMB_GEMM_STAGES");
             env_stages = e ? atoi(e) : 0;
         }
-        if (env_stages > 0 && env_stages <= 16 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024 / (kAwq ? GemmCfg<MPAD>::kCtasAwq : 1) - 1024)
-            p.stages = env_stages;
+        if (env_stages > 0 && env_stages <= 16 && (env_stages % 2) == 0 && GemmCfg<MPAD>::smem_bytes(kAwq, env_stages) <= 227 * 1024)
+            p.stages = env_stages;                                   // even: see the static_assert on the ring depths
     }
     p.trace = trace_for_this_launch();
     const int smem = GemmCfg<MPAD>::smem_bytes(kAwq, p.stages);
@@ -1284,7 +1286,7 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     UMB_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0 && (ldx % 8) == 0 && ldx >= K);
     if (M > 128) return UMB_ERR_UNSUPPORTED;
     if (M > kMaxRowsPerLaunch) {
-        // 65..128 rows run as two launches of <= 64 rows (see kMaxRowsPerLaunch).
+        // only with -DUMB_MAX_ROWS=64: 65..128 rows run as two launches of <= 64 rows
         const int m0 = kMaxRowsPerLaunch;
         umb_epilogue_t e0{}, e1{};
         umb_rope_epilogue_t r1{};
@@ -1346,7 +1348,7 @@ static int gemm_common(bool awq, const void* x, int64_t ldx, const void* w, int6
     const int mpad = mpad_of(M);
     const long long U = (long long)p.tiles * p.units_per_tile;
     if (U >= (1ll << 31)) return UMB_ERR_UNSUPPORTED;
-    int grid = sm_count() * ((awq && mpad <= 32) ? UMB_AWQ_CTAS : 1);
+    int grid = sm_count();
     if ((long long)grid > U) grid = (int)U;
     static int aligned_split = -1;                   // UMB_GEMM_ALIGNED_SPLIT=0: plain stream-K for small problems too (tuning)
     if (aligned_split < 0) {

@@ -6,6 +6,14 @@
 
 #include <utility>
 
+// Token rows one GEMM launch takes (and the forward drivers' chunk size).  Round 1 held this at 64 because the
+// 128-column AWQ instantiation died about once in 150-300 launches; the cause (a parity wait that could run two phases
+// ahead of its barrier in the 4-deep ring) was found and fixed in round 2 -- profiles/r2_m128_root_cause.txt.
+// -DUMB_MAX_ROWS=64 restores the split into two launches.
+#ifndef UMB_MAX_ROWS
+#define UMB_MAX_ROWS 128
+#endif
+
 namespace umb {
 // Programmatic dependent launch (PDL): every kernel of the forward chain is launched with the
 // programmatic-stream-serialization attribute, so its CTAs may start (barrier init, TMEM allocation,

@@ -32,7 +32,7 @@ from .. import _lib, ops
 from .llama import MAX_ROWS, Llama, LlamaAwq
 
 _ALIGN = 256
-CHUNK_ROWS = 64      # rows per chunk of a paged forward (matches kChunkRows of csrc/forward.cu)
+CHUNK_ROWS = 128     # rows per chunk of a paged forward (matches kChunkRows of csrc/forward.cu)
 _PARTS = ("wqkv", "wo", "wgu", "wdown", "input_norm", "post_norm")
 
 
