@@ -13,6 +13,7 @@ scripted acceptance with the reference's DEFAULT_ACC (random weights make draft 
   static8b       (configs[1] / code_config_24gb.json) Llama-3.1-8B fp16 target + 1B draft, 8b_sequoia_tree-5x6 (31 nodes)
   stochastic32k  (configs[3]) 70B-AWQ + 1B, T = 0.6 / top-p 0.9 / top-k 32 / repetition penalty 1.05 (chat_config_48gb),
                  prompt 30000, max_length 32768, KV pages of the upper layers resident in pinned host memory
+  stochastic32k_hbm  the same with the whole KV cache in HBM
 
 A *step* is one speculative-decoding iteration (draft build_tree + target verify + accept + KV gather).  ``value`` =
 accepted tokens / device time over exactly K steps with everything resident in HBM (CUDA events; max over ranks);
@@ -55,6 +56,10 @@ WORKLOADS = {
                                "verify (T 0.6, top-p 0.9, top-k 32, repetition penalty 1.05), prompt 30000, generation 256, "
                                "max_length 32768, KV pages of layers 40..79 in pinned host memory"),
 }
+# the same 32k-context stochastic workload with the whole KV cache resident in HBM (10.7 GB): what the paging costs
+WORKLOADS["stochastic32k_hbm"] = dict(WORKLOADS["stochastic32k"], kv_host_layers=0,
+                                      text=WORKLOADS["stochastic32k"]["text"].replace(
+                                          "KV pages of layers 40..79 in pinned host memory", "KV cache resident in HBM"))
 E2E_REQUESTS = 8          # per replica (2 for stochastic32k: a 30k-token prefill and PCIe-bound verifies per request)
 
 
@@ -208,7 +213,7 @@ def run_ours(args):
     e2e_tokens, e2e_steps = 0, 0
     torch.cuda.synchronize()
     t0 = time.time()
-    n_req = 2 if args.workload == "stochastic32k" else E2E_REQUESTS
+    n_req = 2 if args.workload.startswith("stochastic32k") else E2E_REQUESTS
     for _ in range(n_req):
         out = eng.generate(input_ids=prompt_host, max_new_tokens=GEN)
         e2e_tokens += len(out["generated_tokens"])

@@ -881,8 +881,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                         uint32_t a[16];
 #pragma unroll
                         for (int w = 0; w < 4; ++w) dequant_word(words[w], magic, ce, neg_co, s2, &a[w * 4]);
-                        if (c == 0 && mine >= kAStages) {
-                            // the unit that last used this tensor-memory stage (mine - kAStages) must have retired
+                        UMB_TMEM_ST_X16(taddr + c * 16, a);
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full + ts);
+                    if (mine + kDq < n_units) {            // this group's next unit v: (dq_st, dq_ph) already point at it
+                        // (1) The unit that last used v's tensor-memory stage (v - kAStages) must have retired before the
+                        //     stage is overwritten.
+                        // (2) The same wait makes the parity wait on full_w sound.  A parity wait lets a waiter through that
+                        //     is TWO uses ahead of its barrier (the parity of "use j - 2 completed" equals that of "use j
+                        //     completed"), and the previous occupant of v's shared-memory stage, unit v - kStages, belongs to
+                        //     another group: with the 4-deep ring of the 128-column instantiation it is unit mine - 1, which
+                        //     may still be in flight.  The group then read a stale record and signalled a_full early, the MMA
+                        //     retired early, and the producer re-armed full_w while its previous copy was still open: the
+                        //     "Warp Illegal Instruction" that killed one 128-row launch in ~150 (profiles/r2_m128_root_cause.txt).
+                        //     done[v - kAStages] implies done[v - kStages]: both ring depths are even, so the two units were
+                        //     issued and committed, in order, by the same MMA thread; a retired occupant has landed, so
+                        //     full_w is at most one use behind.  (v < kAStages: first use of both stages, nothing to wait for.)
+                        if (mine + kDq >= kAStages) {
                             UMB_WAIT(done + w_st, w_ph);
                             tc_fence_after();
                             w_st += kDq;
@@ -891,25 +909,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                                 w_ph ^= 1;
                             }
                         }
-                        UMB_TMEM_ST_X16(taddr + c * 16, a);
-                    }
-                    tc_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(a_full + ts);
-                    if (mine + kDq < n_units) {            // this group's next unit: (dq_st, dq_ph) already point at it
-                        // A parity wait is only sound if the waiter cannot be TWO phases ahead of the barrier: waiting for
-                        // use j of a stage while use j - 1 is still in flight passes at once (the parity of "j - 2
-                        // completed" equals that of "j completed").  The previous occupant of this stage is unit
-                        // mine + kDq - kStages, which belongs to another group and may not even have landed yet when the
-                        // ring is as short as 4 stages (the 128-column instantiation: unit mine - 1) -- the group then read a
-                        // stale record, signalled a_full early, and the producer re-armed a barrier whose phase was still
-                        // open: the "Warp Illegal Instruction" (mbarrier arrive on an exhausted phase) that killed about
-                        // one 128-row launch in 150 (profiles/r2_m128_root_cause.txt).  Waiting for the previous occupant to
-                        // have RETIRED first closes it: the producer has waited for every done[] up to unit mine - kStages
-                        // in order before it issued `mine`, so this done[] wait can be at most one phase ahead, and once it
-                        // passes, full_w is at most one phase behind.
-                        if (mine + kDq >= kStages) UMB_WAIT(done + dq_st, dq_ph ^ 1);
                         UMB_WAIT(full_w + (kPair ? (dq_st & ~1) : dq_st), dq_ph);
                         fetch(dq_st);
                     }
