@@ -14,6 +14,7 @@ scripted acceptance with the reference's DEFAULT_ACC (random weights make draft 
   stochastic32k  (configs[3]) 70B-AWQ + 1B, T = 0.6 / top-p 0.9 / top-k 32 / repetition penalty 1.05 (chat_config_48gb),
                  prompt 30000, max_length 32768, KV pages of the upper layers resident in pinned host memory
   stochastic32k_hbm  the same with the whole KV cache in HBM
+  static70b_b200tree the default workload on the packaged B200-tuned 16-node tree (sequoia_utils.generate_budget_tree)
 
 A *step* is one speculative-decoding iteration (draft build_tree + target verify + accept + KV gather).  ``value`` =
 accepted tokens / device time over exactly K steps with everything resident in HBM (CUDA events; max over ranks);
@@ -56,6 +57,11 @@ WORKLOADS = {
                                "verify (T 0.6, top-p 0.9, top-k 32, repetition penalty 1.05), prompt 30000, generation 256, "
                                "max_length 32768, KV pages of layers 40..79 in pinned host memory"),
 }
+# the default workload on the packaged B200-tuned tree (sequoia_utils.generate_budget_tree(16, 4): as many nodes as the
+# 16-row padding of the verify pass holds, the same number of draft levels) -- NOT the configuration the metric is quoted on
+WORKLOADS["static70b_b200tree"] = dict(WORKLOADS["static70b"], tree="b200_sequoia_tree-16.json",
+                                       text=WORKLOADS["static70b"]["text"].replace("sequoia_tree-3x4 (13 nodes)",
+                                                                                   "b200_sequoia_tree-16 (16 nodes, depth 4)"))
 # the same 32k-context stochastic workload with the whole KV cache resident in HBM (10.7 GB): what the paging costs
 WORKLOADS["stochastic32k_hbm"] = dict(WORKLOADS["stochastic32k"], kv_host_layers=0,
                                       text=WORKLOADS["stochastic32k"]["text"].replace(

@@ -20,11 +20,12 @@ from umbrella_b200.speculation.static_speculation_engine import StaticSpeculatio
 
 dev = "cuda:0"
 layers = int(os.environ.get("LAYERS", "4"))
-eng = StaticSpeculationEngine("draft", "target", device=dev, growmap_path=bench.TREE, max_length=bench.MAX_LENGTH,
+WL = bench.WORKLOADS["static70b"]
+eng = StaticSpeculationEngine("draft", "target", device=dev, growmap_path=WL["tree"], max_length=WL["max_length"],
                               temperature=0.0)
-target = L.SyntheticLlama(L.LLAMA31_70B, max_length=bench.MAX_LENGTH, awq=True, seed=1234, device=dev, gen_device=dev,
+target = L.SyntheticLlama(L.LLAMA31_70B, max_length=WL["max_length"], awq=True, seed=1234, device=dev, gen_device=dev,
                           num_layers=layers)
-draft = L.SyntheticLlama(L.LLAMA32_1B, max_length=bench.MAX_LENGTH, awq=False, seed=4321, device=dev, gen_device=dev)
+draft = L.SyntheticLlama(L.LLAMA32_1B, max_length=WL["max_length"], awq=False, seed=4321, device=dev, gen_device=dev)
 eng.initialize(draft_model=draft, target_model=target)
 eng._set_eos([])
 eng.graph_iteration = os.environ.get("GRAPH", "0") == "1"

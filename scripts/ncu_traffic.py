@@ -29,6 +29,6 @@ second = awq[1::2]                                   # the second launch of each
 traffic = sum(rd + wr for rd, wr in second) / len(second)
 json.dump({"awq_gemm_traffic_bytes_per_launch": traffic, "launches_averaged": len(second),
            "per_shape_read_bytes": [rd for rd, _ in second], "per_shape_write_bytes": [wr for _, wr in second],
-           "source": "profiles/r1_ncu_kernels_session4.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
+           "source": out_txt + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"},
           open(out_json, "w"), indent=1)
 print("\n".join(lines)); print("traffic per AWQ launch", traffic)

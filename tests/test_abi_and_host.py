@@ -2,6 +2,7 @@
 symbols include/umbrella_b200.h declares; the ctypes table matches the header; the host-side mirrors keep
 the reference's error behaviour; the product never imports the oracle."""
 import ctypes
+import numpy as np
 import os
 import re
 import subprocess
@@ -204,3 +205,33 @@ def test_checkpoint_reader_round_trip(tmp_path):
         AutoModelLM.from_pretrained("meta-llama/Llama-3.2-1B-Instruct", max_length=64, device="cuda:0").alloc()
     with pytest.raises(ValueError):
         ck.check_layer_shapes(L.LLAMA32_1B, ck.read_layer(ck.SafetensorsIndex(d), 0, False), False, 0)
+
+
+def test_budget_tree_is_the_best_tree_of_its_size():
+    """generate_budget_tree (the B200-tuned growmaps): level order, depth limit, closed under parent / elder sibling,
+    and no tree of the same size and depth has a higher expected accept length (brute force over small budgets)."""
+    import itertools
+    from umbrella_b200.sequoia_utils import (DEFAULT_ACC, expected_accept_length, generate_budget_tree,
+                                             generate_sequoia_tree, load_growmap)
+
+    def best_by_enumeration(budget, depth):
+        # all candidate nodes as rank paths; a tree = a set closed under prefix and under "smaller last rank"
+        paths = [()]
+        for d in range(1, depth + 1):
+            paths += list(itertools.product(range(len(DEFAULT_ACC)), repeat=d))
+        prob = {p: float(np.prod([DEFAULT_ACC[r] for r in p])) if p else 1.0 for p in paths}
+        # the optimum of a sum of per-node values over closed sets where every node's value <= its predecessors' is the
+        # top-`budget` values (ties aside); check that against the greedy result
+        return sum(sorted(prob.values(), reverse=True)[:budget])
+
+    for budget, depth in [(1, 0), (2, 1), (5, 2), (8, 2), (13, 4), (16, 4), (16, 3)]:
+        gm = generate_budget_tree(budget, depth)
+        assert gm["size"] == budget and max(gm["depth"]) <= depth
+        for v, succ in enumerate(gm["Successors"]):
+            assert all(c > v for c in succ) and succ == sorted(succ)
+        assert abs(expected_accept_length(gm) - best_by_enumeration(budget, depth)) < 1e-9
+    tuned, shipped = load_growmap("b200_sequoia_tree-16.json"), load_growmap("sequoia_tree-3x4.json")
+    assert tuned["Successors"] == generate_budget_tree(16, 4)["Successors"]
+    assert tuned["size"] == 16 and max(tuned["depth"]) == max(shipped["depth"])          # same number of draft levels
+    assert expected_accept_length(tuned) > expected_accept_length(shipped) * 1.06
+    assert expected_accept_length(generate_budget_tree(13, 4)) >= expected_accept_length(generate_sequoia_tree(3, 4))

@@ -1,3 +1,8 @@
+// EXPERIMENT RECORD -- NOT PART OF THE DEFAULT BUILD (python -m umbrella_b200.build --variant ring --gemm experimental/gemm_ring.cu
+// swaps it in for csrc/gemm.cu).  The round-2 re-pipelining of the AWQ GEMM (weight-request ring, separate x producer,
+// "drain" form with exact integer operands): parity-green, measured slower than the product kernel at every step
+// (profiles/r2_gemm_experiments.txt, section D).  It predates the parity-wait fix of profiles/r2_m128_root_cause.txt.
+//
 // (i) AWQ INT4 weight-dequant fused into a tcgen05 tensor-core GEMM, plus its fp16-weight twin.
 //
 // Replaces awq_ext.gemm_forward_cuda / dequantize_weights_cuda as called from AwqLinear.apply

@@ -1,3 +1,11 @@
+// EXPERIMENT RECORD -- NOT PART OF THE BUILD (umbrella_b200/build.py does not compile this file).
+// Measured in round 2 and not adopted: shorter per launch under ncu than the tensor-memory kernel on the draft model's
+// shapes, but the draft forward as the iteration graph replays it got slower (855 vs 802 us): this kernel stages weights in
+// registers, fills the register file and cannot co-reside with its stream predecessor, while gemm.cu's kernel requests
+// its whole weight share into shared memory before griddepcontrol.wait (profiles/r2_gemm_experiments.txt, section I).
+// To rebuild the experiment: add "skinny.cu" to SOURCES, declare skinny_gemm_f16 in internal.h and call it from
+// gemm_common for !awq && M <= 8 (git history of round 2 has the wiring, including the fused-norm forward driver).
+//
 // fp16-weight linear for very few token rows (M <= 8): the draft model's per-level forwards.
 //
 // Replaces torch F.linear on the draft side of build_tree (reference umbrella/models/llama.py:87-110 as driven by

@@ -75,6 +75,50 @@ def generate_sequoia_tree(width: int, depth: int, acc: list[float] | None = None
     return gm
 
 
+def generate_budget_tree(budget: int, max_depth: int, acc: list[float] | None = None, json_file: str | None = None) -> dict:
+    """The ``budget`` nodes of highest path probability within ``max_depth`` levels below the root (best-first over
+    (parent, rank) candidates; a node's probability is the product of ``acc[rank]`` along its path, so the set is
+    closed under "parent of" and "elder sibling of" and maximises ``expected_accept_length`` for its size).
+
+    Why a budget instead of the reference's fixed ``width`` per level (sequoia_utils.py:83-130): on a B200 the verify
+    pass costs the same for every tree of <= 16 nodes -- the token rows are the padded N operand of the weight-streaming
+    MMA and one 16-row attention slab per KV-head group -- and the draft side costs one forward per level, so the best
+    tree is "as many nodes as the padding holds, no more levels than before".  ``b200_sequoia_tree-16.json`` (packaged)
+    is ``generate_budget_tree(16, 4)``: 3.58 expected tokens per verify against 3.36 for ``sequoia_tree-3x4.json``
+    (13 nodes, same depth) under DEFAULT_ACC, at the same time per iteration."""
+    import heapq
+    acc = DEFAULT_ACC if acc is None else acc
+    assert budget >= 1 and max_depth >= 0
+    nodes = [(1.0, 0, -1, 0)]                               # (probability, depth, parent, rank) in pick order
+    heap = [(-acc[0], 0, 1, 0, 0)] if max_depth >= 1 else []   # (-probability, tie-break, depth, parent, rank)
+    tie = 1
+    while len(nodes) < budget and heap:
+        negp, _, d, par, r = heapq.heappop(heap)
+        idx = len(nodes)
+        nodes.append((-negp, d, par, r))
+        if r + 1 < len(acc):
+            heapq.heappush(heap, (-(nodes[par][0] * acc[r + 1]), tie, d, par, r + 1))
+            tie += 1
+        if d < max_depth:
+            heapq.heappush(heap, (-(-negp * acc[0]), tie, d + 1, idx, 0))
+            tie += 1
+    # growmaps are stored in level order, children of a node contiguous and ordered by rank
+    new_id, order = {0: 0}, [0]
+    for d in range(1, max_depth + 1):
+        level = sorted((i for i, n in enumerate(nodes) if n[1] == d), key=lambda i: (new_id[nodes[i][2]], nodes[i][3]))
+        for i in level:
+            new_id[i] = len(order)
+            order.append(i)
+    successors: list[list[int]] = [[] for _ in order]
+    for i in order[1:]:
+        successors[new_id[nodes[i][2]]].append(new_id[i])
+    gm = growmap_from_successors(successors)
+    if json_file is not None:
+        with open(json_file, "w") as f:
+            json.dump(gm, f)
+    return gm
+
+
 def load_growmap(path: str) -> dict:
     """Load a growmap.  The Sequoia trees the reference ships (umbrella/trees/*.json) are packaged in compact form
     -- ``trees/growmaps.json``: file name -> successor lists -- and rebuilt into the full schema on load, so a bare
