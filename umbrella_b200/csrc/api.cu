@@ -43,16 +43,15 @@ int arg_fail(const char* file, int line, const char* what) {
     return UMB_ERR_ARG;
 }
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    // cached per device ordinal: one process may drive several GPUs (benign race: every thread computes the same value)
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
     }
-    return cached;
+    return cached[dev];
 }
 }  // namespace umb
 

@@ -657,19 +657,14 @@ template <int D, bool kSoftCap>
 static int launch_attn(const AttnParams& p, bool slab, dim3 grid, cudaStream_t st) {
     if (slab) {
         const size_t smem = (size_t)4 * 4 * kSBN * D * sizeof(__half);          // 4 warps x 2 stages x (K|V)
-        static bool attr_done = false;
-        if (!attr_done && smem > 48 * 1024) {
+        // per-device attribute (a process may drive several GPUs): set on every launch, it is a cheap host call
+        if (smem > 48 * 1024)
             UMB_CUDA(cudaFuncSetAttribute(tree_attn_slab_kernel<D, kSoftCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
         UMB_LAUNCH_PDL(tree_attn_slab_kernel<D, kSoftCap>, grid, dim3(kAttnThreads), smem, st, p);
     } else {
         const size_t smem = (size_t)4 * kBN * D * sizeof(__half);
-        static bool attr_done = false;
-        if (!attr_done && smem > 48 * 1024) {
+        if (smem > 48 * 1024)
             UMB_CUDA(cudaFuncSetAttribute(tree_attn_kernel<D, kSoftCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
         UMB_LAUNCH_PDL(tree_attn_kernel<D, kSoftCap>, grid, dim3(kAttnThreads), smem, st, p);
     }
     int launches = 1;

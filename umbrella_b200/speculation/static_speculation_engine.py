@@ -409,6 +409,7 @@ class StaticSpeculationEngine(BaseEngine):
             if (is_sentence_complete_regex(text[-1]) and done_len >= max_new_tokens - self.stop_distance) \
                     or done_len >= max_new_tokens:
                 decode = False
+        print(" ".join(text[pos:]) if steps else "", flush=True)   # the last words (static...:252)
         torch.cuda.synchronize()
         t2 = time.time()
         return self.num_nodes - start + 1, t2 - t1, steps
@@ -471,11 +472,14 @@ class StaticSpeculationEngine(BaseEngine):
                 return
             success = self.prefill(context)
         else:
+            if len(input_ids) == 0 or max_new_tokens == 0:          # static...:459-464
+                yield "", ""
+                return
             ids = torch.as_tensor(input_ids, dtype=torch.int64).to(self.device)
             success = self._prefill(input_ids=ids.reshape(1, -1))
         if not success:
             self.reset()
-            yield "", ""
+            yield "Exceeding reserved allowed context length", "Exceeding reserved allowed context length"   # static...:469
             return
         torch.cuda.synchronize()
         t1 = time.time()
