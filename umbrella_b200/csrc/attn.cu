@@ -387,8 +387,17 @@ __device__ __forceinline__ uint32_t row_window32(const AttnParams& p, int tok, b
     return allow & exist;
 }
 
-template <int D, bool kSoftCap>
-__global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const AttnParams p) {
+// kWarps = 4: every warp owns a double-buffered ring.  kWarps = 8 (short contexts: 2-3 tiles per warp instead of 4-5, the
+// K/V loads of the whole range in flight at once): double-buffered while the rings fit in shared memory (D = 64),
+// single-buffered otherwise (D = 128: 8 x 16 KB).  The merge is done by the first four warps.
+template <int D, int kWarps>
+struct SlabCfg {
+    static constexpr int kRing = (kWarps * 4 * kSBN * D * (int)sizeof(__half) <= 160 * 1024) ? 2 : 1;
+    static constexpr size_t kSmem = (size_t)kWarps * kRing * 2 * kSBN * D * sizeof(__half);
+};
+template <int D, bool kSoftCap, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) tree_attn_slab_kernel(const AttnParams p) {
+    constexpr int kRing = SlabCfg<D, kWarps>::kRing;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_launch_dependents();
     pdl_wait();
@@ -398,8 +407,8 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const Attn
     const int rows_total = p.qo * p.G;
     const int prefix_len = p.dyn ? p.dyn[0] + p.prefix_len : p.prefix_len;
     const int kv_len = p.dyn ? p.dyn[0] + p.kv_len : p.kv_len;
-    // per-warp ring: [2 stages][K | V][kSBN][D]
-    __half* ring = reinterpret_cast<__half*>(smem_raw) + warp * (4 * kSBN * D);
+    // per-warp ring: [kRing stages][K | V][kSBN][D]
+    __half* ring = reinterpret_cast<__half*>(smem_raw) + warp * (kRing * 2 * kSBN * D);
 
     const int row_base = blockIdx.x * 16;
     int row[2], tok[2];
@@ -452,12 +461,12 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const Attn
         load_tile_warp<D>(ring + kSBN * D, vg, p.kv_tok_stride, tile * kSBN, kv_hi, lane);
         cp_async_commit();
     }
-    for (int it = 0; tile < tile_hi; tile += 4, ++it) {
-        const int buf = it & 1;
-        if (tile + 4 < tile_hi) {
+    for (int it = 0; tile < tile_hi; tile += kWarps, ++it) {
+        const int buf = kRing == 2 ? (it & 1) : 0;
+        if (kRing == 2 && tile + kWarps < tile_hi) {
             __half* nxt = ring + (buf ^ 1) * (2 * kSBN * D);
-            load_tile_warp<D>(nxt, kg, p.kv_tok_stride, (tile + 4) * kSBN, kv_hi, lane);
-            load_tile_warp<D>(nxt + kSBN * D, vg, p.kv_tok_stride, (tile + 4) * kSBN, kv_hi, lane);
+            load_tile_warp<D>(nxt, kg, p.kv_tok_stride, (tile + kWarps) * kSBN, kv_hi, lane);
+            load_tile_warp<D>(nxt + kSBN * D, vg, p.kv_tok_stride, (tile + kWarps) * kSBN, kv_hi, lane);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -552,14 +561,19 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const Attn
             }
         }
         __syncwarp();
+        if (kRing == 1 && tile + kWarps < tile_hi) {       // single buffer: the next tile is requested once this one is consumed
+            load_tile_warp<D>(ring, kg, p.kv_tok_stride, (tile + kWarps) * kSBN, kv_hi, lane);
+            load_tile_warp<D>(ring + kSBN * D, vg, p.kv_tok_stride, (tile + kWarps) * kSBN, kv_hi, lane);
+            cp_async_commit();
+        }
     }
 
-    // ---- merge the four warps' partials through shared memory ----
+    // ---- merge the warps' partials through shared memory (first 128 threads) ----
     __syncthreads();                                   // every warp is done with its ring
     constexpr int kLd = D + 4;                         // padded fp32 row
-    float* s_o = reinterpret_cast<float*>(smem_raw);   // [4][16][kLd]
-    float* s_m = s_o + 4 * 16 * kLd;                   // [4][16]
-    float* s_l = s_m + 64;                             // [4][16]
+    float* s_o = reinterpret_cast<float*>(smem_raw);   // [kWarps][16][kLd]
+    float* s_m = s_o + kWarps * 16 * kLd;              // [kWarps][16]
+    float* s_l = s_m + kWarps * 16;                    // [kWarps][16]
 #pragma unroll
     for (int ri = 0; ri < 2; ++ri) {
         const int r = g4 + 8 * ri;
@@ -573,18 +587,18 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const Attn
         }
     }
     __syncthreads();
-    {
+    if (threadIdx.x < 128) {
         const int r = threadIdx.x >> 3;                // 16 rows x 8 threads
         const int c0 = (threadIdx.x & 7) * (D / 8);    // D/8 consecutive columns per thread
         const int grow_in_head = row_base + r;
         if (grow_in_head < rows_total) {
             float m = -INFINITY;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) m = fmaxf(m, s_m[w * 16 + r]);
+            for (int w = 0; w < kWarps; ++w) m = fmaxf(m, s_m[w * 16 + r]);
             const float m_use = m == -INFINITY ? 0.f : m;
-            float wgt[4], l = 0.f;
+            float wgt[kWarps], l = 0.f;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < kWarps; ++w) {
                 wgt[w] = exp2f(s_m[w * 16 + r] - m_use);
                 l += s_l[w * 16 + r] * wgt[w];
             }
@@ -596,7 +610,7 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const Attn
                 for (int c = 0; c < D / 8; c += 2) {
                     float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
+                    for (int w = 0; w < kWarps; ++w) {
                         v0 += s_o[(w * 16 + r) * kLd + c0 + c] * wgt[w];
                         v1 += s_o[(w * 16 + r) * kLd + c0 + c + 1] * wgt[w];
                     }
@@ -609,7 +623,7 @@ __global__ void __launch_bounds__(kAttnThreads) tree_attn_slab_kernel(const Attn
                 for (int c = 0; c < D / 8; ++c) {
                     float v = 0.f;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) v += s_o[(w * 16 + r) * kLd + c0 + c] * wgt[w];
+                    for (int w = 0; w < kWarps; ++w) v += s_o[(w * 16 + r) * kLd + c0 + c] * wgt[w];
                     orow[c] = v;
                 }
                 if ((threadIdx.x & 7) == 0) p.part_ml[grow] = make_float2(m, l);
@@ -653,14 +667,21 @@ extern "C" size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int hea
     return 32 * rows * ((size_t)head_dim * sizeof(float) + sizeof(float2)) + 256;
 }
 
+template <int D, bool kSoftCap, int kWarps>
+static int launch_slab(const AttnParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = SlabCfg<D, kWarps>::kSmem;
+    // per-device attribute (a process may drive several GPUs): set on every launch, it is a cheap host call
+    if (smem > 48 * 1024)
+        UMB_CUDA(cudaFuncSetAttribute(tree_attn_slab_kernel<D, kSoftCap, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UMB_LAUNCH_PDL((tree_attn_slab_kernel<D, kSoftCap, kWarps>), grid, dim3(kWarps * 32), smem, st, p);
+    return UMB_OK;
+}
+
 template <int D, bool kSoftCap>
-static int launch_attn(const AttnParams& p, bool slab, dim3 grid, cudaStream_t st) {
+static int launch_attn(const AttnParams& p, bool slab, int slab_warps, dim3 grid, cudaStream_t st) {
     if (slab) {
-        const size_t smem = (size_t)4 * 4 * kSBN * D * sizeof(__half);          // 4 warps x 2 stages x (K|V)
-        // per-device attribute (a process may drive several GPUs): set on every launch, it is a cheap host call
-        if (smem > 48 * 1024)
-            UMB_CUDA(cudaFuncSetAttribute(tree_attn_slab_kernel<D, kSoftCap>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        UMB_LAUNCH_PDL(tree_attn_slab_kernel<D, kSoftCap>, grid, dim3(kAttnThreads), smem, st, p);
+        const int rc = slab_warps == 8 ? launch_slab<D, kSoftCap, 8>(p, grid, st) : launch_slab<D, kSoftCap, 4>(p, grid, st);
+        if (rc != UMB_OK) return rc;
     } else {
         const size_t smem = (size_t)4 * kBN * D * sizeof(__half);
         if (smem > 48 * 1024)
@@ -747,8 +768,18 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
         p.part_ml = reinterpret_cast<float2*>(base + (size_t)splits * rows * head_dim * sizeof(float));
     }
     const dim3 grid(slab ? slabs : (rows_total + kBM - 1) / kBM, p.Hkv, splits);
+    // slab CTAs of 8 warps when each warp would otherwise walk more than two tiles (UMB_ATTN_WARPS=4 / 8: tuning override)
+    static int warps_override = -1;
+    if (warps_override < 0) {
+        const char* e = getenv("UMB_ATTN_WARPS");
+        warps_override = e ? atoi(e) : 0;
+    }
+    const int tiles_per_cta = (kv_tiles + splits - 1) / splits;
+    int slab_warps = tiles_per_cta > 8 ? 8 : 4;
+    if (warps_override == 4 || warps_override == 8) slab_warps = warps_override;
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 128)
-        return soft_cap > 0.f ? launch_attn<128, true>(p, slab, grid, st) : launch_attn<128, false>(p, slab, grid, st);
-    return soft_cap > 0.f ? launch_attn<64, true>(p, slab, grid, st) : launch_attn<64, false>(p, slab, grid, st);
+        return soft_cap > 0.f ? launch_attn<128, true>(p, slab, slab_warps, grid, st)
+                              : launch_attn<128, false>(p, slab, slab_warps, grid, st);
+    return soft_cap > 0.f ? launch_attn<64, true>(p, slab, slab_warps, grid, st) : launch_attn<64, false>(p, slab, slab_warps, grid, st);
 }
