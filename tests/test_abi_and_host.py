@@ -230,8 +230,18 @@ def test_budget_tree_is_the_best_tree_of_its_size():
         for v, succ in enumerate(gm["Successors"]):
             assert all(c > v for c in succ) and succ == sorted(succ)
         assert abs(expected_accept_length(gm) - best_by_enumeration(budget, depth)) < 1e-9
-    tuned, shipped = load_growmap("b200_sequoia_tree-16.json"), load_growmap("sequoia_tree-3x4.json")
-    assert tuned["Successors"] == generate_budget_tree(16, 4)["Successors"]
-    assert tuned["size"] == 16 and max(tuned["depth"]) == max(shipped["depth"])          # same number of draft levels
-    assert expected_accept_length(tuned) > expected_accept_length(shipped) * 1.06
+    from umbrella_b200.sequoia_utils import tune_budget_tree
+    shipped = load_growmap("sequoia_tree-3x4.json")
+    same_depth = load_growmap("b200_sequoia_tree-16-depth4.json")
+    assert same_depth["Successors"] == generate_budget_tree(16, 4)["Successors"]
+    assert same_depth["size"] == 16 and max(same_depth["depth"]) == max(shipped["depth"])   # same number of draft levels
+    assert expected_accept_length(same_depth) > expected_accept_length(shipped) * 1.06
     assert expected_accept_length(generate_budget_tree(13, 4)) >= expected_accept_length(generate_sequoia_tree(3, 4))
+    # the packaged tuned tree is the optimum of the measured two-parameter cost model: one level fewer
+    tuned, rate = tune_budget_tree(16, fixed_ms=10.0, draft_forward_ms=1.05)
+    assert load_growmap("b200_sequoia_tree-16.json")["Successors"] == tuned["Successors"]
+    assert tuned["size"] == 16 and max(tuned["depth"]) == 3
+    shipped_rate = 1e3 * expected_accept_length(shipped) / (10.0 + 1.05 * 4)
+    assert rate > 1.08 * shipped_rate
+    # a free draft model wants the deepest tree, an expensive one the shallowest
+    assert max(tune_budget_tree(16, 10.0, 0.0)[0]["depth"]) > max(tune_budget_tree(16, 10.0, 20.0)[0]["depth"])

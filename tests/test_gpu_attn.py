@@ -32,7 +32,10 @@ def _check(out, ref):
     ("sequoia_tree-3x4.json", 64, 8, 128, 5),
     ("8b_sequoia_tree-5x6.json", 32, 8, 128, 300),
     ("8b_sequoia_tree-6x7.json", 32, 8, 64, 1000),
-    ("sequoia_tree-3x4.json", 8, 1, 128, 4100),       # long context -> split-KV + merge
+    ("sequoia_tree-3x4.json", 8, 1, 128, 4100),       # long context -> split-KV + merge (tcgen05 kernel from 4096 rows)
+    ("sequoia_tree-3x4.json", 64, 8, 128, 9000),      # tcgen05 kernel, 8 kv heads x 18 splits, last tile ragged
+    ("sequoia_tree-3x4.json", 32, 8, 128, 6011),      # G = 4: 52 of the 128 tile rows in use
+    ("sequoia_tree-3x4.json", 64, 8, 128, 4083),      # tree rows straddle a 128-row tile boundary
 ])
 def test_tree_mask_modes(tree_name, Hq, Hkv, D, prefix):
     from umbrella_b200 import ops
@@ -59,7 +62,8 @@ def test_tree_mask_modes(tree_name, Hq, Hkv, D, prefix):
     _check(out3.cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("qo,prefix,Hq,Hkv,D", [(128, 0, 8, 2, 128), (77, 130, 32, 8, 64), (1, 600, 64, 8, 128)])
+@pytest.mark.parametrize("qo,prefix,Hq,Hkv,D", [(128, 0, 8, 2, 128), (77, 130, 32, 8, 64), (1, 600, 64, 8, 128),
+                                                (16, 5000, 64, 8, 128), (3, 4500, 8, 1, 128)])     # tcgen05 kernel
 def test_causal(qo, prefix, Hq, Hkv, D):
     from umbrella_b200 import ops
     rng = np.random.default_rng(5)

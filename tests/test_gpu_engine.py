@@ -57,7 +57,9 @@ def _ar_greedy(model, prompt, n_new):
 
 @pytest.mark.parametrize("tree,draft_same,graph", [("sequoia_tree-3x4.json", False, False),
                                                    ("sequoia_tree-3x4.json", False, True),
-                                                   ("8b_sequoia_tree-5x6.json", True, True)])
+                                                   ("8b_sequoia_tree-5x6.json", True, True),
+                                                   ("b200_sequoia_tree-16.json", False, True),      # tune_budget_tree(16, 10.0, 1.05): depth 3
+                                                   ("b200_sequoia_tree-16-depth4.json", True, False)])
 def test_greedy_speculation_is_lossless(tree, draft_same, graph):
     """graph=True runs every iteration as one captured CUDA graph (several buckets of 128 positions)."""
     eng = _engine(tree, draft_same=draft_same, graph=graph)

@@ -13,6 +13,7 @@
 // The mask is never materialised for the tree case: rows see [0, prefix_len) unconditionally and
 // prefix_len + j iff bit j of their ancestor bitmask is set.  Long contexts are split along KV
 // (grid.z) and merged by a second kernel with a log-sum-exp reduction.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -632,6 +633,323 @@ __global__ void __launch_bounds__(kWarps * 32) tree_attn_slab_kernel(const AttnP
     }
 }
 
+#ifdef UMB_ATTN_TC   // unfinished tcgen05 long-context kernel: variant builds only (csrc/experimental/attn_tc.cu has the notes)
+// ------------------------------------------------------------------------------------------------
+// Long-context variant on the 5th-generation tensor cores (head_dim 128, <= 128 flattened query rows: every tree of
+// <= 16 nodes at G = 8): one CTA per (kv split, kv head) holds ALL query rows of the head group as one 128-row UMMA
+// tile, so every K/V byte is read once per CTA and the two GEMMs run at tcgen05 rate instead of the legacy mma.sync
+// rate that bounds the kernels above at long context (profiles/r2_hmma_rate_b200.txt: a quarter of it).
+//   warp 4      TMA producer: K and V tiles of 128 kv rows ([2 atoms][128 rows][128 B], 128-byte swizzle) through
+//               3-D tensor maps over the cache (d, kv head, kv row), two stages
+//   warp 5      MMA issuer: S = Q K^T (A = Q and B = K from shared memory, both K-major, accumulator in tensor memory,
+//               double-buffered), O += P V (A = P from TENSOR memory, B = the V tile as it lies in the cache, i.e.
+//               MN-major: LBO = the 64-d atom stride, SBO = 1024 B between 8-row groups -- pinned by umb_probe_umma mode 2)
+//   warps 0..3  one thread per query row: tcgen05.ld of its S row, mask, online softmax in fp32 (no shuffles: the row
+//               is the thread's), P as fp16 pairs back to tensor memory with tcgen05.st, O rescaled in tensor memory when
+//               the running maximum of any row of the warp moved
+// Tensor memory (512 columns): S0 | S1 (128 each) | O (128) | P0 | P1 (64 each).  Partials (m, l, O) per split go to the
+// same workspace layout as the kernels above and are merged by tree_attn_combine_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcT = 128;                       // kv rows per tile
+constexpr int kTcThreads = 192;
+constexpr int kTcTileBytes = kTcT * 256;        // one K (or V) tile: 2 atoms x 128 rows x 128 B
+constexpr int kTcSmem = 1024 + 32768 + 2 * 2 * kTcTileBytes + 256;
+
+#ifdef UMB_ATTN_TC_DEBUG
+// debugging build: every wait of block (0, 0) leaves its source line in a host-mapped progress buffer, one slot per warp
+// (low bit 8 set = still waiting), so that a hang can be read from the host while the kernel is stuck
+__device__ unsigned long long* g_tc_dbg = nullptr;
+__device__ __forceinline__ void tc_mark(int slot, unsigned long long v) {
+    if (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0) {
+        g_tc_dbg[slot] = v;
+        __threadfence_system();
+    }
+}
+__device__ __forceinline__ void tc_wait_dbg(int line, uint64_t* bar, uint32_t parity) {
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) tc_mark(w, ((unsigned long long)line << 32) | 0x100u | parity);
+    mbar_wait(bar, parity);
+    if ((threadIdx.x & 31) == 0) tc_mark(w, ((unsigned long long)line << 32) | parity);
+}
+#define TC_WAIT(line, bar, parity) tc_wait_dbg(line, bar, parity)
+#define TC_MARK(slot, v) do { if ((threadIdx.x & 31) == 0) tc_mark(slot, v); } while (0)
+#else
+#define TC_WAIT(line, bar, parity) mbar_wait(bar, parity)
+#define TC_MARK(slot, v) do { } while (0)
+#endif
+__global__ void __launch_bounds__(kTcThreads, 1)
+tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                    const AttnParams p) {
+    constexpr int D = 128;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* s_q = smem;                                  // [2 atoms][128 rows][128 B]
+    unsigned char* s_kv = smem + 32768;                         // [2 stages][K | V][kTcTileBytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + 2 * 2 * kTcTileBytes);
+    uint64_t* k_full = bars;            // [2]
+    uint64_t* v_full = bars + 2;        // [2]
+    uint64_t* kv_empty = bars + 4;      // [2]  both tiles of the stage consumed (PV retired)
+    uint64_t* s_full = bars + 6;        // [2]  S buffer written (QK retired)
+    uint64_t* s_empty = bars + 8;       // [2]  S buffer read by the four softmax warps
+    uint64_t* p_full = bars + 10;       // [2]  P buffer written, O rescaled
+    uint64_t* o_ready = bars + 12;      //      PV of a tile retired
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, hkv = blockIdx.y;
+    const int rows_total = p.qo * p.G;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(k_full + i, 1);
+            mbar_init(v_full + i, 1);
+            mbar_init(kv_empty + i, 1);
+            mbar_init(s_full + i, 1);
+            mbar_init(s_empty + i, 4);
+            mbar_init(p_full + i, 4);
+        }
+        mbar_init(o_ready, 1);
+        fence_barrier_init();
+    }
+    TC_MARK(8 + warp, 1);
+    if (warp == 5) {
+        tmem_alloc(s_tmem, 512);
+        tmem_relinquish();
+    }
+    TC_MARK(8 + warp, 2);
+    pdl_launch_dependents();
+    pdl_wait();                                 // q and the appended K/V rows are the predecessors' output
+    TC_MARK(8 + warp, 3);
+    const int prefix_len = p.dyn ? p.dyn[0] + p.prefix_len : p.prefix_len;
+    const int kv_len = p.dyn ? p.dyn[0] + p.kv_len : p.kv_len;
+    int kv_hi = kv_len;
+    if (p.mask_mode == UMB_MASK_CAUSAL)
+        kv_hi = min(kv_hi, prefix_len + (rows_total - 1) / p.G + 1);
+    else if (p.mask_mode == UMB_MASK_TREE)
+        kv_hi = min(kv_hi, prefix_len + p.tree_words * 32);
+    const int n_tiles = (kv_hi + kTcT - 1) / kTcT;
+    const int tiles_per_split = (n_tiles + p.splits - 1) / p.splits;
+    const int tile_lo = split * tiles_per_split;
+    const int tile_hi = min(n_tiles, tile_lo + tiles_per_split);
+    const int n_my = max(tile_hi - tile_lo, 0);
+
+    // Q rows of this head group -> shared memory, K-major with the 128-byte swizzle (row r = token r / G, head r % G)
+    if (warp < 4) {
+        const int r = threadIdx.x;
+        const bool ok = r < rows_total;
+        const __half* qr = p.q + ((int64_t)(ok ? r / p.G : 0) * p.Hq + hkv * p.G + (ok ? r % p.G : 0)) * D;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (ok) v = *reinterpret_cast<const uint4*>(qr + c * 8);
+            *reinterpret_cast<uint4*>(s_q + (c >> 3) * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
+    TC_MARK(8 + warp, 4 | ((unsigned long long)n_my << 8) | ((unsigned long long)tmem << 32));
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        const uint64_t pol = l2_policy_evict_first();
+        for (int i = 0; i < n_my; ++i) {
+            const int st = i & 1, use = i >> 1;
+            if (use > 0) TC_WAIT(__LINE__, kv_empty + st, (use - 1) & 1);
+            if (elect_one()) {
+                const int row0 = (tile_lo + i) * kTcT;
+                unsigned char* kt = s_kv + st * (2 * kTcTileBytes);
+                unsigned char* vt = kt + kTcTileBytes;
+                mbar_arrive_expect_tx(k_full + st, (uint32_t)kTcTileBytes);
+                tma_tensor3d_g2s(kt, &tmap_k, 0, hkv, row0, k_full + st, pol);
+                tma_tensor3d_g2s(kt + kTcT * 128, &tmap_k, 64, hkv, row0, k_full + st, pol);
+                mbar_arrive_expect_tx(v_full + st, (uint32_t)kTcTileBytes);
+                tma_tensor3d_g2s(vt, &tmap_v, 0, hkv, row0, v_full + st, pol);
+                tma_tensor3d_g2s(vt + kTcT * 128, &tmap_v, 64, hkv, row0, v_full + st, pol);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t kIdescQK = umma_idesc_f16(128, kTcT);
+        constexpr uint32_t kIdescPV = umma_idesc_f16(128, D) | (1u << 16);          // B (V) MN-major
+        auto issue_qk = [&](int i) {
+            const int st = i & 1, use = i >> 1;
+            TC_WAIT(__LINE__, k_full + st, use & 1);
+            if (use > 0) TC_WAIT(__LINE__, s_empty + st, (use - 1) & 1);                      // S buffer i & 1 has been read
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t kt = smem_u32(s_kv + st * (2 * kTcTileBytes));
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint64_t ad = umma_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
+                    const uint64_t bd = umma_smem_desc_sw128(kt + (kk >> 2) * (kTcT * 128) + (kk & 3) * 32);
+                    umma_ss_f16(tmem + kColS + st * 128, ad, bd, kIdescQK, kk ? 1u : 0u);
+                }
+                umma_commit(s_full + st);
+            }
+            __syncwarp();
+        };
+        if (n_my > 0) issue_qk(0);
+        for (int i = 0; i < n_my; ++i) {
+            if (i + 1 < n_my) issue_qk(i + 1);
+            const int st = i & 1, use = i >> 1;
+            TC_WAIT(__LINE__, v_full + st, use & 1);
+            TC_WAIT(__LINE__, p_full + st, use & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t vt = smem_u32(s_kv + st * (2 * kTcTileBytes) + kTcTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    uint64_t bd = 0;
+                    bd |= (uint64_t)(((vt + kk * 2048) & 0x3FFFF) >> 4);              // 16 kv rows per k-step
+                    bd |= (uint64_t)((kTcT * 128) >> 4) << 16;                        // LBO: next 64-d atom
+                    bd |= (uint64_t)(1024 >> 4) << 32;                                // SBO: next group of 8 kv rows
+                    bd |= (uint64_t)1 << 46;
+                    bd |= (uint64_t)2 << 61;
+                    umma_ts_f16(tmem + kColO, tmem + kColP + st * 64 + kk * 8, bd, kIdescPV, (i > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(kv_empty + st);
+                umma_commit(o_ready);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax: thread = query row =====================
+        const int r = threadIdx.x;
+        const bool row_ok = r < rows_total;
+        const int tok = row_ok ? r / p.G : 0;
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int i = 0; i < n_my; ++i) {
+            const int st = i & 1, use = i >> 1;
+            const int col0 = (tile_lo + i) * kTcT;
+            const bool need_mask = (col0 + kTcT > kv_hi) || (col0 + kTcT > prefix_len) || !row_ok;
+            TC_WAIT(__LINE__, s_full + st, use & 1);
+            tc_fence_after();
+            const uint32_t s_addr = tmem + lane_addr + kColS + st * 128;
+            uint32_t win[4] = {~0u, ~0u, ~0u, ~0u};
+            if (need_mask) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) win[c] = row_window32(p, tok, row_ok, col0 + 32 * c, kv_hi, prefix_len);
+            }
+            // pass 1: row maximum
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                UMB_TMEM_LD_X32(s_addr + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if ((win[c] >> j) & 1u) mx = fmaxf(mx, __uint_as_float(v[j]));
+            }
+            const float m_new = fmaxf(m_run, mx * p.scale_log2);
+            const float m_use = m_new == -INFINITY ? 0.f : m_new;
+            const float corr = exp2f(m_run - m_use);
+            // pass 2: probabilities -> P (fp16 pairs, the A operand of the PV product)
+            float l_tile = 0.f;
+            const uint32_t p_addr = tmem + lane_addr + kColP + st * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32], pk[16];
+                UMB_TMEM_LD_X32(s_addr + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float p0 = ((win[c] >> (2 * j)) & 1u) ? exp2f(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_use)) : 0.f;
+                    const float p1 = ((win[c] >> (2 * j + 1)) & 1u) ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_use)) : 0.f;
+                    l_tile += p0 + p1;
+                    pk[j] = pack_half2(p0, p1);
+                }
+                UMB_TMEM_ST_X16(p_addr + c * 16, pk);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + st);            // this warp's 32 rows of S are consumed
+            // O so far belongs to the previous maximum: rescale it once the previous PV has retired
+            if (i > 0) {
+                TC_WAIT(__LINE__, o_ready, (i - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, corr != 1.f)) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t v[32];
+                        UMB_TMEM_LD_X32(tmem + lane_addr + kColO + c * 32, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * corr);
+                        UMB_TMEM_ST_X32(tmem + lane_addr + kColO + c * 32, v);
+                    }
+                }
+            }
+            l_run = l_run * corr + l_tile;
+            m_run = m_new;
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full + st);
+        }
+        // ---- output: the normalised rows (one split) or the (m, l, O) partial of this split ----
+        if (n_my > 0) {
+            TC_WAIT(__LINE__, o_ready, (n_my - 1) & 1);
+            tc_fence_after();
+        }
+        {
+            // every lane executes the tensor-memory loads (.sync.aligned: a partially active warp is undefined behaviour --
+            // the rows past rows_total of the last warp hung the first version here); only the stores are predicated
+            const int hq = hkv * p.G + (row_ok ? r % p.G : 0);
+            const float inv = (p.splits == 1) ? (l_run > 0.f ? 1.f / l_run : 0.f) : 1.f;
+            __half* orow = p.out + ((int64_t)tok * p.Hq + hq) * D;
+            const int64_t grow = (int64_t)split * p.Hkv * rows_total + (int64_t)hkv * rows_total + (row_ok ? r : 0);
+            float* prow = p.splits == 1 ? nullptr : p.part_o + grow * D;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                if (n_my > 0) {
+                    UMB_TMEM_LD_X32(tmem + lane_addr + kColO + c * 32, v);
+                    tc_wait_ld();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (!row_ok) continue;
+                if (p.splits == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 o;
+                        o.x = pack_half2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+                        o.y = pack_half2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+                        o.z = pack_half2(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
+                        o.w = pack_half2(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(prow + c * 32 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+            }
+            if (row_ok && p.splits > 1) p.part_ml[grow] = make_float2(m_run, l_run);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+
+#endif
+
 // grid (Hkv * qo * G); block D threads.  Merges the per-split (m, l, o) triples.
 template <int D>
 __global__ void __launch_bounds__(D) tree_attn_combine_kernel(const AttnParams p) {
@@ -660,12 +978,61 @@ __global__ void __launch_bounds__(D) tree_attn_combine_kernel(const AttnParams p
 
 using namespace umb;
 
+#ifdef UMB_ATTN_TC_DEBUG
+extern "C" int umb_debug_attn_tc_ptr(void* host_mapped) {
+    unsigned long long* p = (unsigned long long*)host_mapped;
+    return (int)cudaMemcpyToSymbol(umb::g_tc_dbg, &p, sizeof(p));
+}
+#endif
+
 extern "C" size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int head_dim, int max_kv_len) {
     (void)max_kv_len;
     if (qo < 1 || num_q_heads < 1 || head_dim < 1) return 0;
     const size_t rows = (size_t)qo * num_q_heads;
     return 32 * rows * ((size_t)head_dim * sizeof(float) + sizeof(float2)) + 256;
 }
+
+#ifdef UMB_ATTN_TC
+// 3-D tensor map over a K (or V) cache plane: (d, kv head, kv row) with the caller's strides, box [64 d, 1 head, 128 rows],
+// 128-byte swizzle -- one box is one 64-d atom of a tile as tcgen05.mma reads it.
+typedef CUresult (*PFN_encodeTiledAttn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tmap_kv(CUtensorMap* map, const void* base, int D, int Hkv, int64_t rows, int64_t tok_stride,
+                        int64_t head_stride) {
+    static PFN_encodeTiledAttn enc = nullptr;
+    if (!enc) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return UMB_ERR_DRIVER;
+        enc = reinterpret_cast<PFN_encodeTiledAttn>(sym);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Hkv, (cuuint64_t)rows};
+    const cuuint64_t strides[2] = {(cuuint64_t)head_stride * sizeof(__half), (cuuint64_t)tok_stride * sizeof(__half)};
+    const cuuint32_t box[3] = {64, 1, (cuuint32_t)kTcT};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? UMB_OK : arg_fail(__FILE__, __LINE__, "cuTensorMapEncodeTiled(kv)");
+}
+
+// Long contexts on the tensor-memory kernel: head_dim 128, all query rows of a head group in one 128-row tile, implicit
+// masks only.  UMB_ATTN_TC=0 switches it off, UMB_ATTN_TC_MIN_KV moves the threshold (tuning).
+static int attn_tc_min_kv() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* off = getenv("UMB_ATTN_TC");
+        const char* e = getenv("UMB_ATTN_TC_MIN_KV");
+        cached = (off && off[0] == '0') ? (1 << 30) : (e ? atoi(e) : 4096);
+    }
+    return cached;
+}
+
+
+#endif
 
 template <int D, bool kSoftCap, int kWarps>
 static int launch_slab(const AttnParams& p, dim3 grid, cudaStream_t st) {
@@ -736,6 +1103,45 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
     p.scale_log2 = p.sm_scale * 1.4426950408889634f;
     p.soft_cap = soft_cap;
 
+#ifdef UMB_ATTN_TC
+    const int rows_total_tc = qo * p.G;
+    if (head_dim == 128 && rows_total_tc <= 128 && soft_cap <= 0.f && mask->mask_mode != UMB_MASK_DENSE &&
+        kv_bound >= attn_tc_min_kv() && (kv_tok_stride * sizeof(__half)) % 16 == 0 && (kv_head_stride * sizeof(__half)) % 16 == 0) {
+        const int n_tiles = (kv_bound + kTcT - 1) / kTcT;
+        int splits = sm_count() / num_kv_heads;
+        splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
+        splits = splits > n_tiles ? n_tiles : splits;
+        const size_t rows = (size_t)qo * num_q_heads;
+        const size_t per_split = rows * ((size_t)head_dim * sizeof(float) + sizeof(float2));
+        if (splits > 1) {
+            const size_t avail = (workspace && workspace_bytes > 256) ? (workspace_bytes - 256) / per_split : 0;
+            if ((size_t)splits > avail) splits = avail < 1 ? 1 : (int)avail;
+        }
+        p.splits = splits;
+        if (splits > 1) {
+            const uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+            p.part_o = reinterpret_cast<float*>(base);
+            p.part_ml = reinterpret_cast<float2*>(base + (size_t)splits * rows * head_dim * sizeof(float));
+        }
+        CUtensorMap tk, tv;
+        int rc = make_tmap_kv(&tk, k_cache, head_dim, num_kv_heads, kv_bound, kv_tok_stride, kv_head_stride);
+        if (rc != UMB_OK) return rc;
+        rc = make_tmap_kv(&tv, v_cache, head_dim, num_kv_heads, kv_bound, kv_tok_stride, kv_head_stride);
+        if (rc != UMB_OK) return rc;
+        cudaStream_t st_tc = (cudaStream_t)stream;
+        UMB_CUDA(cudaFuncSetAttribute(tree_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+        UMB_LAUNCH_PDL(tree_attn_tc_kernel, dim3(splits, num_kv_heads), dim3(kTcThreads), (size_t)kTcSmem, st_tc, tk, tv, p);
+        int launches = 1;
+        if (splits > 1) {
+            UMB_LAUNCH_PDL(tree_attn_combine_kernel<128>, dim3((unsigned)(p.Hkv * p.qo * p.G)), dim3(128), 0, st_tc, p);
+            launches = 2;
+        }
+        count_launches(launches);
+        UMB_LAUNCH_CHECK();
+        return UMB_OK;
+    }
+
+#endif
     // kernel + split selection.  slab kernel: K/V is re-read once per 16-row slab (L2), so it is used
     // while that re-read is cheap; long contexts with many slabs go to the 64-row tile kernel.
     const int rows_total = qo * p.G;

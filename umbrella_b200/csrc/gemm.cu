@@ -1141,6 +1141,71 @@ probe_umma_kernel(const __half* __restrict__ a, const __half* __restrict__ b, fl
     }
 }
 
+// probe: D[128, 128] = A[128, 64 k] * Bt[64 k, 128 n] with the B operand MN-major (n contiguous in memory, as the V rows
+// of a KV cache are): Bt is staged as two 64-n atoms of [64 k rows][128 B], 128-byte swizzled -- the image a TMA box
+// [64 n, 64 k rows] would leave -- and described with LBO = the atom stride along n, SBO = 1024 B between 8-row k groups
+// (mode 2), or with the two swapped (mode 3: the reading that must NOT work).
+__global__ void __launch_bounds__(128, 1)
+probe_umma_mn_kernel(const __half* __restrict__ a, const __half* __restrict__ bt, float* __restrict__ d, int mode) {
+    __shared__ __align__(1024) unsigned char s_a[128 * 128];
+    __shared__ __align__(1024) unsigned char s_b[2 * 64 * 128];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, r = threadIdx.x;
+    for (int c = 0; c < 8; ++c) {
+        const uint4 va = *reinterpret_cast<const uint4*>(a + r * 64 + c * 8);
+        *reinterpret_cast<uint4*>(s_a + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = va;
+    }
+    for (int i = r; i < 2 * 64 * 8; i += 128) {                 // (atom, k row, 16-byte chunk)
+        const int atom = i / (64 * 8), row = (i / 8) % 64, c = i % 8;
+        const uint4 vb = *reinterpret_cast<const uint4*>(bt + row * 128 + atom * 64 + c * 8);
+        *reinterpret_cast<uint4*>(s_b + atom * 8192 + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)) = vb;
+    }
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(&s_tmem, 128);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = umma_idesc_f16(128, 128) | (1u << 16);      // B MN-major
+        const uint64_t lbo = mode == 2 ? 8192 : 1024, sbo = mode == 2 ? 1024 : 8192;
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = umma_smem_desc_sw128(smem_u32(s_a) + kk * 32);
+            uint64_t bd = 0;
+            bd |= (uint64_t)(((smem_u32(s_b) + kk * 2048) & 0x3FFFF) >> 4);    // 16 k rows = two 8-row groups further
+            bd |= (uint64_t)(lbo >> 4) << 16;
+            bd |= (uint64_t)(sbo >> 4) << 32;
+            bd |= (uint64_t)1 << 46;
+            bd |= (uint64_t)2 << 61;
+            umma_ss_f16(tmem, ad, bd, idesc, kk ? 1u : 0u);
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t rr[16];
+        UMB_TMEM_LD_X16(tmem + lane_addr + c0, rr);
+        tc_wait_ld();
+        for (int j = 0; j < 16; ++j) d[r * 128 + c0 + j] = __uint_as_float(rr[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 128);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT cross-check of the packed stream (tests only): one CTA per tile, thread = feature row.
 // ------------------------------------------------------------------------------------------------
@@ -1489,8 +1554,11 @@ extern "C" int umb_debug_gemm_trace(unsigned long long* host_out, int max_ctas) 
 }
 
 extern "C" int umb_probe_umma(const void* a, const void* b, float* d, int mode, umb_stream_t stream) {
-    UMB_CHECK_ARG(a && b && d && (mode == 0 || mode == 1));
-    probe_umma_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, d, mode);
+    UMB_CHECK_ARG(a && b && d && mode >= 0 && mode <= 3);
+    if (mode >= 2)      // B operand MN-major: b is fp16 [64 k, 128 n], d fp32 [128, 128]
+        probe_umma_mn_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, d, mode);
+    else
+        probe_umma_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, d, mode);
     count_launches(1);
     UMB_LAUNCH_CHECK();
     return UMB_OK;

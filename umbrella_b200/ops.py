@@ -156,7 +156,7 @@ def gemm_f16(x: torch.Tensor, w: torch.Tensor, *, mode: int = UMB_EPI_STORE, bia
 
 
 def probe_umma(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
-    d = torch.empty((128, 16), dtype=torch.float32, device=a.device)
+    d = torch.empty((128, 128 if mode >= 2 else 16), dtype=torch.float32, device=a.device)
     check(_lib.load().umb_probe_umma(_p(a), _p(b), _p(d), mode, _stream()), "probe_umma")
     return d
 

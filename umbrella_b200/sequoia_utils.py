@@ -83,9 +83,7 @@ def generate_budget_tree(budget: int, max_depth: int, acc: list[float] | None = 
     Why a budget instead of the reference's fixed ``width`` per level (sequoia_utils.py:83-130): on a B200 the verify
     pass costs the same for every tree of <= 16 nodes -- the token rows are the padded N operand of the weight-streaming
     MMA and one 16-row attention slab per KV-head group -- and the draft side costs one forward per level, so the best
-    tree is "as many nodes as the padding holds, no more levels than before".  ``b200_sequoia_tree-16.json`` (packaged)
-    is ``generate_budget_tree(16, 4)``: 3.58 expected tokens per verify against 3.36 for ``sequoia_tree-3x4.json``
-    (13 nodes, same depth) under DEFAULT_ACC, at the same time per iteration."""
+    tree is "as many nodes as the padding holds" at the depth ``tune_budget_tree`` picks from the measured costs."""
     import heapq
     acc = DEFAULT_ACC if acc is None else acc
     assert budget >= 1 and max_depth >= 0
@@ -117,6 +115,27 @@ def generate_budget_tree(budget: int, max_depth: int, acc: list[float] | None = 
         with open(json_file, "w") as f:
             json.dump(gm, f)
     return gm
+
+
+def tune_budget_tree(budget: int, fixed_ms: float, draft_forward_ms: float, acc: list[float] | None = None,
+                     max_depth: int = 8, lazy_leaf: bool = True) -> tuple[dict, float]:
+    """The budget tree whose depth maximises expected accepted tokens per second under a two-parameter cost model of one
+    iteration: ``fixed_ms`` (target verify + accept + gathers: flat in the tree size up to the 16-row padding) plus one
+    draft forward of ``draft_forward_ms`` per level below the root that is fed to the draft model (the leaf level is
+    not, with the lazily computed leaf K/V).  Returns (growmap, predicted tokens per second).
+
+    Measured on a B200 for the 70B-AWQ target + 1B draft: fixed 10.0 ms, 1.05 ms per draft forward ->
+    depth 3, ``b200_sequoia_tree-16.json`` (packaged): 3.43 expected tokens per verify in 13.2 ms against 3.36 in 14.2 ms
+    for ``sequoia_tree-3x4.json`` (13 nodes, depth 4)."""
+    best, best_rate = None, -1.0
+    for depth in range(1, max_depth + 1):
+        gm = generate_budget_tree(budget, depth, acc)
+        levels = max(gm["depth"])                                  # a small budget may not reach `depth`
+        forwards = levels if lazy_leaf else levels + 1
+        rate = 1e3 * expected_accept_length(gm, acc) / (fixed_ms + draft_forward_ms * max(forwards, 1))
+        if rate > best_rate + 1e-12:
+            best, best_rate = gm, rate
+    return best, best_rate
 
 
 def load_growmap(path: str) -> dict:
