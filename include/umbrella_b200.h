@@ -244,7 +244,8 @@ int umb_topk_f32(const float* logits, int64_t ld, int rows, int vocab, int k, fl
 /* decode the UMB_EPI_LOGITS arg-max keys into int64 token ids */
 int umb_argmax_keys_to_ids(const unsigned long long* keys, int rows, int64_t* out, umb_stream_t stream);
 
-/* Debug probes (tests only): one 128x16x64 UMMA with A from tensor memory / shared memory. */
+/* Debug probes (tests only): one 128x16x64 UMMA with A from shared memory (mode 0) / tensor memory (mode 1); modes 2, 3:
+ * b is fp16 [64 k, 128 n] (MN-major B operand), d fp32 [128, 128] -- the two readings of the operand descriptor. */
 int umb_probe_umma(const void* a /*fp16 [128,64]*/, const void* b /*fp16 [16,64]*/, float* d /*[128,16]*/, int mode,
                    umb_stream_t stream);
 

@@ -40,6 +40,19 @@ def test_probe_umma(mode):
     assert torch.allclose(d, ref, atol=1e-3, rtol=1e-4), (d - ref).abs().max()
 
 
+def test_probe_umma_mn_major_operand():
+    """tcgen05.mma with an MN-major B operand (the way V rows lie in a KV cache): LBO = stride between 64-element atoms
+    along N, SBO = 1024 B between 8-row groups along K.  The swapped reading (mode 3) must be wrong."""
+    from umbrella_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(128, 64, generator=g).to(torch.float16)
+    bt = torch.randn(64, 128, generator=g).to(torch.float16)          # [k, n], n contiguous
+    ref = a.float() @ bt.float()
+    d = ops.probe_umma(a.to(DEV), bt.to(DEV), 2).cpu()
+    assert d.shape == (128, 128) and torch.allclose(d, ref, atol=1e-3, rtol=1e-4), (d - ref).abs().max()
+    assert (ops.probe_umma(a.to(DEV), bt.to(DEV), 3).cpu() - ref).abs().max() > 1.0
+
+
 def test_repack_unpack_dequantize_bit_exact():
     from umbrella_b200 import ops
     golden = np.load(os.path.join(GOLDEN, "awq_pack.npz"))
