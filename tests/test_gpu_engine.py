@@ -84,6 +84,20 @@ def test_greedy_speculation_is_lossless(tree, draft_same, graph):
         assert int(lg.argmax()) == toks[0]
 
 
+def test_greedy_speculation_is_lossless_at_long_context():
+    """Prompt of 8250 tokens: the target's verify attention (26 query rows, head_dim 128) runs on the tensor-memory
+    long-context kernel with the device-resident prefix length of the iteration graph; output must equal plain greedy
+    decoding through the same forward."""
+    eng = _engine(S=8704, graph=True)
+    g = torch.Generator().manual_seed(17)
+    prompt = torch.randint(3, TARGET.vocab_size, (8250,), generator=g)
+    n_new = 24
+    ref = _ar_greedy(eng.target_model, prompt, n_new + 8)
+    out = eng.generate(input_ids=prompt.tolist(), max_new_tokens=n_new)
+    toks = out["generated_tokens"]
+    assert len(toks) >= n_new and toks == ref[:len(toks)]
+
+
 def test_scripted_acceptance_matches_oracle_bookkeeping():
     """Scripted run: accept lengths / tokens / positions follow the oracle's verify_step exactly."""
     from umbrella_b200.speculation.scripted import ScriptedAcceptance

@@ -633,28 +633,40 @@ __global__ void __launch_bounds__(kWarps * 32) tree_attn_slab_kernel(const AttnP
     }
 }
 
-#ifdef UMB_ATTN_TC   // unfinished tcgen05 long-context kernel: variant builds only (csrc/experimental/attn_tc.cu has the notes)
+#ifndef UMB_ATTN_TC
+#define UMB_ATTN_TC 1   // 0: build without the tensor-memory long-context kernel
+#endif
+#if UMB_ATTN_TC
 // ------------------------------------------------------------------------------------------------
 // Long-context variant on the 5th-generation tensor cores (head_dim 128, <= 128 flattened query rows: every tree of
 // <= 16 nodes at G = 8): one CTA per (kv split, kv head) holds ALL query rows of the head group as one 128-row UMMA
 // tile, so every K/V byte is read once per CTA and the two GEMMs run at tcgen05 rate instead of the legacy mma.sync
 // rate that bounds the kernels above at long context (profiles/r2_hmma_rate_b200.txt: a quarter of it).
-//   warp 4      TMA producer: K and V tiles of 128 kv rows ([2 atoms][128 rows][128 B], 128-byte swizzle) through
-//               3-D tensor maps over the cache (d, kv head, kv row), two stages
+//   warp 4      TMA producer: K and V tiles of 64 kv rows ([2 atoms][64 rows][128 B], 128-byte swizzle) through
+//               3-D tensor maps over the cache (d, kv head, kv row), a 5-deep ring (128 KB in flight ahead of the consumer)
 //   warp 5      MMA issuer: S = Q K^T (A = Q and B = K from shared memory, both K-major, accumulator in tensor memory,
 //               double-buffered), O += P V (A = P from TENSOR memory, B = the V tile as it lies in the cache, i.e.
 //               MN-major: LBO = the 64-d atom stride, SBO = 1024 B between 8-row groups -- pinned by umb_probe_umma mode 2)
-//   warps 0..3  one thread per query row: tcgen05.ld of its S row, mask, online softmax in fp32 (no shuffles: the row
-//               is the thread's), P as fp16 pairs back to tensor memory with tcgen05.st, O rescaled in tensor memory when
-//               the running maximum of any row of the warp moved
-// Tensor memory (512 columns): S0 | S1 (128 each) | O (128) | P0 | P1 (64 each).  Partials (m, l, O) per split go to the
+//   warps 0..3  one thread per query row: ONE tcgen05.ld of its 64-column S row, mask (skipped inside the committed
+//               prefix), online softmax in fp32 (no shuffles: the row is the thread's; ex2.approx), P as fp16 pairs back to
+//               tensor memory with tcgen05.st; the reference exponent is lazy (moves only when a tile exceeds it by 2^8),
+//               so O in tensor memory is rescaled a handful of times per row instead of on every tile
+// Tensor memory: S0 | S1 (64 columns each) | O (128, at column 256) | P0 | P1 (32 each, at 384).  Partials (m, l, O) per split go to the
 // same workspace layout as the kernels above and are merged by tree_attn_combine_kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTcT = 128;                       // kv rows per tile
+constexpr int kTcT = 64;                        // kv rows per tile
+constexpr int kTcKv = 5;                        // K/V ring depth: 4 tiles (128 KB) in flight ahead of the one being consumed
+constexpr int kTcChunks = kTcT / 32;            // 32-column chunks of a score row
 constexpr int kTcThreads = 192;
-constexpr int kTcTileBytes = kTcT * 256;        // one K (or V) tile: 2 atoms x 128 rows x 128 B
-constexpr int kTcSmem = 1024 + 32768 + 2 * 2 * kTcTileBytes + 256;
+constexpr int kTcTileBytes = kTcT * 256;        // one K (or V) tile: 2 atoms x kTcT rows x 128 B
+constexpr int kTcSmem = 1024 + 32768 + kTcKv * 2 * kTcTileBytes + 256;
 
+// 2^x on the special-function unit (ex2.approx.ftz: 2 ulp, the arguments are <= 0 here; -inf -> 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 #ifdef UMB_ATTN_TC_DEBUG
 // debugging build: every wait of block (0, 0) leaves its source line in a host-mapped progress buffer, one slot per warp
 // (low bit 8 set = still waiting), so that a hang can be read from the host while the kernel is stuck
@@ -684,16 +696,16 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* s_q = smem;                                  // [2 atoms][128 rows][128 B]
-    unsigned char* s_kv = smem + 32768;                         // [2 stages][K | V][kTcTileBytes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + 2 * 2 * kTcTileBytes);
-    uint64_t* k_full = bars;            // [2]
-    uint64_t* v_full = bars + 2;        // [2]
-    uint64_t* kv_empty = bars + 4;      // [2]  both tiles of the stage consumed (PV retired)
-    uint64_t* s_full = bars + 6;        // [2]  S buffer written (QK retired)
-    uint64_t* s_empty = bars + 8;       // [2]  S buffer read by the four softmax warps
-    uint64_t* p_full = bars + 10;       // [2]  P buffer written, O rescaled
-    uint64_t* o_ready = bars + 12;      //      PV of a tile retired
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 13);
+    unsigned char* s_kv = smem + 32768;                         // [kTcKv stages][K | V][kTcTileBytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + kTcKv * 2 * kTcTileBytes);
+    uint64_t* k_full = bars;            // [kTcKv]
+    uint64_t* v_full = bars + 8;        // [kTcKv]
+    uint64_t* kv_empty = bars + 16;     // [kTcKv]  both tiles of the stage consumed (PV retired)
+    uint64_t* s_full = bars + 24;       // [2]  S buffer written (QK retired)
+    uint64_t* s_empty = bars + 26;      // [2]  S buffer read by the four softmax warps
+    uint64_t* p_full = bars + 28;       // [2]  P buffer written, O rescaled
+    uint64_t* o_ready = bars + 30;      //      PV of a tile retired
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 31);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, hkv = blockIdx.y;
@@ -702,10 +714,12 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_v);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kTcKv; ++i) {
             mbar_init(k_full + i, 1);
             mbar_init(v_full + i, 1);
             mbar_init(kv_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(s_full + i, 1);
             mbar_init(s_empty + i, 4);
             mbar_init(p_full + i, 4);
@@ -759,7 +773,7 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         // ===================== TMA producer =====================
         const uint64_t pol = l2_policy_evict_first();
         for (int i = 0; i < n_my; ++i) {
-            const int st = i & 1, use = i >> 1;
+            const int st = i % kTcKv, use = i / kTcKv;
             if (use > 0) TC_WAIT(__LINE__, kv_empty + st, (use - 1) & 1);
             if (elect_one()) {
                 const int row0 = (tile_lo + i) * kTcT;
@@ -779,9 +793,9 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         constexpr uint32_t kIdescQK = umma_idesc_f16(128, kTcT);
         constexpr uint32_t kIdescPV = umma_idesc_f16(128, D) | (1u << 16);          // B (V) MN-major
         auto issue_qk = [&](int i) {
-            const int st = i & 1, use = i >> 1;
+            const int st = i % kTcKv, use = i / kTcKv, sb = i & 1, su = i >> 1;
             TC_WAIT(__LINE__, k_full + st, use & 1);
-            if (use > 0) TC_WAIT(__LINE__, s_empty + st, (use - 1) & 1);                      // S buffer i & 1 has been read
+            if (su > 0) TC_WAIT(__LINE__, s_empty + sb, (su - 1) & 1);                        // S buffer i & 1 has been read
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t kt = smem_u32(s_kv + st * (2 * kTcTileBytes));
@@ -789,30 +803,30 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 for (int kk = 0; kk < 8; ++kk) {
                     const uint64_t ad = umma_smem_desc_sw128(smem_u32(s_q) + (kk >> 2) * 16384 + (kk & 3) * 32);
                     const uint64_t bd = umma_smem_desc_sw128(kt + (kk >> 2) * (kTcT * 128) + (kk & 3) * 32);
-                    umma_ss_f16(tmem + kColS + st * 128, ad, bd, kIdescQK, kk ? 1u : 0u);
+                    umma_ss_f16(tmem + kColS + sb * kTcT, ad, bd, kIdescQK, kk ? 1u : 0u);
                 }
-                umma_commit(s_full + st);
+                umma_commit(s_full + sb);
             }
             __syncwarp();
         };
         if (n_my > 0) issue_qk(0);
         for (int i = 0; i < n_my; ++i) {
             if (i + 1 < n_my) issue_qk(i + 1);
-            const int st = i & 1, use = i >> 1;
+            const int st = i % kTcKv, use = i / kTcKv, sb = i & 1, su = i >> 1;
             TC_WAIT(__LINE__, v_full + st, use & 1);
-            TC_WAIT(__LINE__, p_full + st, use & 1);
+            TC_WAIT(__LINE__, p_full + sb, su & 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t vt = smem_u32(s_kv + st * (2 * kTcTileBytes) + kTcTileBytes);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
+                for (int kk = 0; kk < kTcT / 16; ++kk) {
                     uint64_t bd = 0;
                     bd |= (uint64_t)(((vt + kk * 2048) & 0x3FFFF) >> 4);              // 16 kv rows per k-step
                     bd |= (uint64_t)((kTcT * 128) >> 4) << 16;                        // LBO: next 64-d atom
                     bd |= (uint64_t)(1024 >> 4) << 32;                                // SBO: next group of 8 kv rows
                     bd |= (uint64_t)1 << 46;
                     bd |= (uint64_t)2 << 61;
-                    umma_ts_f16(tmem + kColO, tmem + kColP + st * 64 + kk * 8, bd, kIdescPV, (i > 0 || kk > 0) ? 1u : 0u);
+                    umma_ts_f16(tmem + kColO, tmem + kColP + sb * (kTcT / 2) + kk * 8, bd, kIdescPV, (i > 0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(kv_empty + st);
                 umma_commit(o_ready);
@@ -827,48 +841,64 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
         float m_run = -INFINITY, l_run = 0.f;
         for (int i = 0; i < n_my; ++i) {
-            const int st = i & 1, use = i >> 1;
+            const int st = i & 1, use = i >> 1;             // S / P buffer and its use count
             const int col0 = (tile_lo + i) * kTcT;
             const bool need_mask = (col0 + kTcT > kv_hi) || (col0 + kTcT > prefix_len) || !row_ok;
             TC_WAIT(__LINE__, s_full + st, use & 1);
             tc_fence_after();
-            const uint32_t s_addr = tmem + lane_addr + kColS + st * 128;
-            uint32_t win[4] = {~0u, ~0u, ~0u, ~0u};
+            const uint32_t s_addr = tmem + lane_addr + kColS + st * kTcT;
+            uint32_t win[kTcChunks];
+#pragma unroll
+            for (int c = 0; c < kTcChunks; ++c) win[c] = ~0u;
             if (need_mask) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) win[c] = row_window32(p, tok, row_ok, col0 + 32 * c, kv_hi, prefix_len);
+                for (int c = 0; c < kTcChunks; ++c) win[c] = row_window32(p, tok, row_ok, col0 + 32 * c, kv_hi, prefix_len);
             }
-            // pass 1: row maximum
+            // the whole score row (kTcT = 64 columns) in ONE tensor-memory load, kept in registers for both passes
+            static_assert(kTcT == 64, "the softmax below holds one 64-column row per thread");
+            uint32_t v[64];
+            UMB_TMEM_LD_X64(s_addr, v);
+            tc_wait_ld();
+            // pass 1: row maximum.  Tiles inside the committed prefix need no mask: the common case at long context runs
+            // without the per-element window tests.
             float mx = -INFINITY;
+            if (need_mask) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                UMB_TMEM_LD_X32(s_addr + c * 32, v);
-                tc_wait_ld();
+                for (int j = 0; j < 64; ++j)
+                    if ((win[j >> 5] >> (j & 31)) & 1u) mx = fmaxf(mx, __uint_as_float(v[j]));
+            } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if ((win[c] >> j) & 1u) mx = fmaxf(mx, __uint_as_float(v[j]));
+                for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
             }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
+            // Lazy reference: the exponentials stay relative to the running reference m_run as long as the tile's maximum
+            // exceeds it by less than 2^8 (P <= 256 in fp16, sums in fp32: exact up to rounding) -- O in tensor memory is
+            // rescaled only when the reference really moves, not on every small increase of some row's maximum.
+            const float m_tile = mx * p.scale_log2;
+            const float m_new = (m_tile > m_run + 8.f || m_run == -INFINITY) ? fmaxf(m_run, m_tile) : m_run;
             const float m_use = m_new == -INFINITY ? 0.f : m_new;
-            const float corr = exp2f(m_run - m_use);
+            const float corr = m_new == m_run ? 1.f : exp2f(m_run - m_use);
             // pass 2: probabilities -> P (fp16 pairs, the A operand of the PV product)
             float l_tile = 0.f;
-            const uint32_t p_addr = tmem + lane_addr + kColP + st * 64;
+            const uint32_t p_addr = tmem + lane_addr + kColP + st * (kTcT / 2);
+            uint32_t pk[32];
+            if (need_mask) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32], pk[16];
-                UMB_TMEM_LD_X32(s_addr + c * 32, v);
-                tc_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float p0 = ((win[c] >> (2 * j)) & 1u) ? exp2f(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_use)) : 0.f;
-                    const float p1 = ((win[c] >> (2 * j + 1)) & 1u) ? exp2f(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_use)) : 0.f;
+                for (int j = 0; j < 32; ++j) {
+                    const float p0 = ((win[j >> 4] >> ((2 * j) & 31)) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_use)) : 0.f;
+                    const float p1 = ((win[j >> 4] >> ((2 * j + 1) & 31)) & 1u) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_use)) : 0.f;
                     l_tile += p0 + p1;
                     pk[j] = pack_half2(p0, p1);
                 }
-                UMB_TMEM_ST_X16(p_addr + c * 16, pk);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_use));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_use));
+                    l_tile += p0 + p1;
+                    pk[j] = pack_half2(p0, p1);
+                }
             }
+            UMB_TMEM_ST_X32(p_addr, pk);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + st);            // this warp's 32 rows of S are consumed
@@ -992,7 +1022,7 @@ extern "C" size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int hea
     return 32 * rows * ((size_t)head_dim * sizeof(float) + sizeof(float2)) + 256;
 }
 
-#ifdef UMB_ATTN_TC
+#if UMB_ATTN_TC
 // 3-D tensor map over a K (or V) cache plane: (d, kv head, kv row) with the caller's strides, box [64 d, 1 head, 128 rows],
 // 128-byte swizzle -- one box is one 64-d atom of a tile as tcgen05.mma reads it.
 typedef CUresult (*PFN_encodeTiledAttn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1019,14 +1049,15 @@ static int make_tmap_kv(CUtensorMap* map, const void* base, int D, int Hkv, int6
     return r == CUDA_SUCCESS ? UMB_OK : arg_fail(__FILE__, __LINE__, "cuTensorMapEncodeTiled(kv)");
 }
 
-// Long contexts on the tensor-memory kernel: head_dim 128, all query rows of a head group in one 128-row tile, implicit
-// masks only.  UMB_ATTN_TC=0 switches it off, UMB_ATTN_TC_MIN_KV moves the threshold (tuning).
+// Long contexts (>= 8192 KV rows) go to the tensor-memory kernel: head_dim 128, all query rows of a head group in one
+// 128-row tile, implicit masks only.  Measured against the mma.sync kernels (profiles/r2_attn_long_context.txt): 30.8 vs
+// 33.6 us at 8k, 61.2 vs 80.6 us at 32k.  UMB_ATTN_TC=0 switches it off at run time, UMB_ATTN_TC_MIN_KV moves the threshold.
 static int attn_tc_min_kv() {
     static int cached = -1;
     if (cached < 0) {
         const char* off = getenv("UMB_ATTN_TC");
         const char* e = getenv("UMB_ATTN_TC_MIN_KV");
-        cached = (off && off[0] == '0') ? (1 << 30) : (e ? atoi(e) : 4096);
+        cached = (off && off[0] == '0') ? (1 << 30) : (e ? atoi(e) : 8192);
     }
     return cached;
 }
@@ -1103,7 +1134,7 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
     p.scale_log2 = p.sm_scale * 1.4426950408889634f;
     p.soft_cap = soft_cap;
 
-#ifdef UMB_ATTN_TC
+#if UMB_ATTN_TC
     const int rows_total_tc = qo * p.G;
     if (head_dim == 128 && rows_total_tc <= 128 && soft_cap <= 0.f && mask->mask_mode != UMB_MASK_DENSE &&
         kv_bound >= attn_tc_min_kv() && (kv_tok_stride * sizeof(__half)) % 16 == 0 && (kv_head_stride * sizeof(__half)) % 16 == 0) {
