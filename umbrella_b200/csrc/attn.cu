@@ -1049,15 +1049,16 @@ static int make_tmap_kv(CUtensorMap* map, const void* base, int D, int Hkv, int6
     return r == CUDA_SUCCESS ? UMB_OK : arg_fail(__FILE__, __LINE__, "cuTensorMapEncodeTiled(kv)");
 }
 
-// Long contexts (>= 8192 KV rows) go to the tensor-memory kernel: head_dim 128, all query rows of a head group in one
-// 128-row tile, implicit masks only.  Measured against the mma.sync kernels (profiles/r2_attn_long_context.txt): 30.8 vs
-// 33.6 us at 8k, 61.2 vs 80.6 us at 32k.  UMB_ATTN_TC=0 switches it off at run time, UMB_ATTN_TC_MIN_KV moves the threshold.
+// Contexts of >= 2048 KV rows go to the tensor-memory kernel: head_dim 128, all query rows of a head group in one 128-row
+// tile, implicit masks only.  Measured against the mma.sync kernels (profiles/r2_attn_long_context.txt): 21.9 vs 24.4 us at
+// 2k, 24.8 vs 29.5 at 4k, 30.8 vs 33.6 at 8k, 61.2 vs 80.6 at 32k; slower below (20.1 vs 17.5 us at 1k).
+// UMB_ATTN_TC=0 switches it off at run time, UMB_ATTN_TC_MIN_KV moves the threshold.
 static int attn_tc_min_kv() {
     static int cached = -1;
     if (cached < 0) {
         const char* off = getenv("UMB_ATTN_TC");
         const char* e = getenv("UMB_ATTN_TC_MIN_KV");
-        cached = (off && off[0] == '0') ? (1 << 30) : (e ? atoi(e) : 8192);
+        cached = (off && off[0] == '0') ? (1 << 30) : (e ? atoi(e) : 2048);
     }
     return cached;
 }
