@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from umbrella_b200.speculation.scripted import ScriptedAcceptance
 dev = "cuda:0"
-eng = bench.build_engine(dev, seed=0)
+eng = bench.build_engine(dev, bench.WORKLOADS["static70b"])
 eng.acceptance_script = ScriptedAcceptance(eng.Successors, seed=1, max_iters=4096, device=dev)
 eng.graph_iteration = os.environ.get("GRAPH", "1") == "1"
 prompt = torch.randint(3, 30000, (1, int(os.environ.get("PROMPT", "512"))), device=dev)
