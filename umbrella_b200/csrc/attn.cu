@@ -642,8 +642,8 @@ __global__ void __launch_bounds__(kWarps * 32) tree_attn_slab_kernel(const AttnP
 // <= 16 nodes at G = 8): one CTA per (kv split, kv head) holds ALL query rows of the head group as one 128-row UMMA
 // tile, so every K/V byte is read once per CTA and the two GEMMs run at tcgen05 rate instead of the legacy mma.sync
 // rate that bounds the kernels above at long context (profiles/r2_hmma_rate_b200.txt: a quarter of it).
-//   warp 4      TMA producer: K and V tiles of 64 kv rows ([2 atoms][64 rows][128 B], 128-byte swizzle) through
-//               3-D tensor maps over the cache (d, kv head, kv row), a 5-deep ring (128 KB in flight ahead of the consumer)
+//   warps 4, 6  TMA producers (K tiles / V tiles): tiles of 64 kv rows ([2 atoms][64 rows][128 B], 128-byte swizzle), ONE
+//               request per tile through 4-D tensor maps over the cache (d, kv row, atom, kv head), a 5-deep ring
 //   warp 5      MMA issuer: S = Q K^T (A = Q and B = K from shared memory, both K-major, accumulator in tensor memory,
 //               double-buffered), O += P V (A = P from TENSOR memory, B = the V tile as it lies in the cache, i.e.
 //               MN-major: LBO = the 64-d atom stride, SBO = 1024 B between 8-row groups -- pinned by umb_probe_umma mode 2)
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(kWarps * 32) tree_attn_slab_kernel(const AttnP
 constexpr int kTcT = 64;                        // kv rows per tile
 constexpr int kTcKv = 5;                        // K/V ring depth: 4 tiles (128 KB) in flight ahead of the one being consumed
 constexpr int kTcChunks = kTcT / 32;            // 32-column chunks of a score row
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 224;                 // 4 softmax warps, K producer, MMA issuer, V producer
 constexpr int kTcTileBytes = kTcT * 256;        // one K (or V) tile: 2 atoms x kTcT rows x 128 B
 constexpr int kTcSmem = 1024 + 32768 + kTcKv * 2 * kTcTileBytes + 256;
 
@@ -678,15 +678,31 @@ __device__ __forceinline__ void tc_mark(int slot, unsigned long long v) {
     }
 }
 __device__ __forceinline__ void tc_wait_dbg(int line, uint64_t* bar, uint32_t parity) {
+#ifdef UMB_ATTN_TC_MARK_WAITS            // progress marks through PCIe: only when hunting a hang
     const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) tc_mark(w, ((unsigned long long)line << 32) | 0x100u | parity);
     mbar_wait(bar, parity);
     if ((threadIdx.x & 31) == 0) tc_mark(w, ((unsigned long long)line << 32) | parity);
+#else
+    (void)line;
+    mbar_wait_spin(bar, parity);
+#endif
 }
 #define TC_WAIT(line, bar, parity) tc_wait_dbg(line, bar, parity)
 #define TC_MARK(slot, v) do { if ((threadIdx.x & 31) == 0) tc_mark(slot, v); } while (0)
+// timeline of the first 12 tiles of block (0, 0): %globaltimer stamps kept in shared memory (8 per tile: softmax warp 0
+// 0..4, MMA warp 5..7) and copied to the host-mapped buffer when the kernel ends -- stamping through PCIe costs
+// microseconds per stamp and measures itself
+__device__ __forceinline__ unsigned long long* tc_stamp_buf() {
+    __shared__ unsigned long long s_stamp[96];
+    return s_stamp;
+}
+#define TC_STAMP(tile, k) do { if ((threadIdx.x & 31) == 0 && (tile) < 12 && blockIdx.x == 0 && blockIdx.y == 0 && \
+                                   ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == 5)) { \
+        unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); tc_stamp_buf()[(tile) * 8 + (k)] = t__; } } while (0)
 #else
-#define TC_WAIT(line, bar, parity) mbar_wait(bar, parity)
+#define TC_STAMP(tile, k) do { } while (0)
+#define TC_WAIT(line, bar, parity) mbar_wait_spin(bar, parity)
 #define TC_MARK(slot, v) do { } while (0)
 #endif
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -769,22 +785,22 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
     constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
     TC_MARK(8 + warp, 4 | ((unsigned long long)n_my << 8) | ((unsigned long long)tmem << 32));
 
-    if (warp == 4) {
-        // ===================== TMA producer =====================
+    if (warp == 4 || warp == 6) {
+        // ===================== TMA producers: warp 4 requests the K tiles, warp 6 the V tiles =====================
+        // One request per 16 KB tile (4-D map: both 64-d atoms in one box) from its own thread: a thread gets a TMA request
+        // out every ~230 ns whatever its size (profiles/r2_tma_rates_b200.txt); four requests per 64-row tile from one
+        // thread WERE the tile period of the first form of this kernel (1.57 us, profiles/r2_attn_long_context.txt).
         const uint64_t pol = l2_policy_evict_first();
+        const bool is_k = warp == 4;
+        const CUtensorMap* tm = is_k ? &tmap_k : &tmap_v;
+        uint64_t* full = is_k ? k_full : v_full;
         for (int i = 0; i < n_my; ++i) {
             const int st = i % kTcKv, use = i / kTcKv;
             if (use > 0) TC_WAIT(__LINE__, kv_empty + st, (use - 1) & 1);
             if (elect_one()) {
-                const int row0 = (tile_lo + i) * kTcT;
-                unsigned char* kt = s_kv + st * (2 * kTcTileBytes);
-                unsigned char* vt = kt + kTcTileBytes;
-                mbar_arrive_expect_tx(k_full + st, (uint32_t)kTcTileBytes);
-                tma_tensor3d_g2s(kt, &tmap_k, 0, hkv, row0, k_full + st, pol);
-                tma_tensor3d_g2s(kt + kTcT * 128, &tmap_k, 64, hkv, row0, k_full + st, pol);
-                mbar_arrive_expect_tx(v_full + st, (uint32_t)kTcTileBytes);
-                tma_tensor3d_g2s(vt, &tmap_v, 0, hkv, row0, v_full + st, pol);
-                tma_tensor3d_g2s(vt + kTcT * 128, &tmap_v, 64, hkv, row0, v_full + st, pol);
+                unsigned char* dst = s_kv + st * (2 * kTcTileBytes) + (is_k ? 0 : kTcTileBytes);
+                mbar_arrive_expect_tx(full + st, (uint32_t)kTcTileBytes);
+                tma_tensor4d_g2s(dst, tm, 0, (tile_lo + i) * kTcT, 0, hkv, full + st, pol);
             }
             __syncwarp();
         }
@@ -813,9 +829,11 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         for (int i = 0; i < n_my; ++i) {
             if (i + 1 < n_my) issue_qk(i + 1);
             const int st = i % kTcKv, use = i / kTcKv, sb = i & 1, su = i >> 1;
+            TC_STAMP(i, 5);
             TC_WAIT(__LINE__, v_full + st, use & 1);
             TC_WAIT(__LINE__, p_full + sb, su & 1);
             tc_fence_after();
+            TC_STAMP(i, 6);
             if (elect_one()) {
                 const uint32_t vt = smem_u32(s_kv + st * (2 * kTcTileBytes) + kTcTileBytes);
 #pragma unroll
@@ -832,6 +850,7 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 umma_commit(o_ready);
             }
             __syncwarp();
+            TC_STAMP(i, 7);
         }
     } else {
         // ===================== softmax: thread = query row =====================
@@ -843,9 +862,14 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         for (int i = 0; i < n_my; ++i) {
             const int st = i & 1, use = i >> 1;             // S / P buffer and its use count
             const int col0 = (tile_lo + i) * kTcT;
-            const bool need_mask = (col0 + kTcT > kv_hi) || (col0 + kTcT > prefix_len) || !row_ok;
+            // warp-uniform on purpose: the rows past qo * G of the last warp run the same unmasked path on their all-zero Q
+            // (never stored) -- with `|| !row_ok` here that warp diverged on every tile, took twice as long as the other
+            // three and set the pace of the whole pipeline (p_full needs all four warps)
+            const bool need_mask = (col0 + kTcT > kv_hi) || (col0 + kTcT > prefix_len);
+            TC_STAMP(i, 0);
             TC_WAIT(__LINE__, s_full + st, use & 1);
             tc_fence_after();
+            TC_STAMP(i, 1);
             const uint32_t s_addr = tmem + lane_addr + kColS + st * kTcT;
             uint32_t win[kTcChunks];
 #pragma unroll
@@ -899,6 +923,7 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
                 }
             }
             UMB_TMEM_ST_X32(p_addr, pk);
+            TC_STAMP(i, 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + st);            // this warp's 32 rows of S are consumed
@@ -906,6 +931,7 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             if (i > 0) {
                 TC_WAIT(__LINE__, o_ready, (i - 1) & 1);
                 tc_fence_after();
+                TC_STAMP(i, 3);
                 if (__any_sync(0xffffffffu, corr != 1.f)) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -924,6 +950,7 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full + st);
+            TC_STAMP(i, 4);
         }
         // ---- output: the normalised rows (one split) or the (m, l, O) partial of this split ----
         if (n_my > 0) {
@@ -975,6 +1002,9 @@ tree_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_con
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+#ifdef UMB_ATTN_TC_DEBUG
+    if (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 96) g_tc_dbg[64 + threadIdx.x] = tc_stamp_buf()[threadIdx.x];
+#endif
 }
 
 
@@ -1023,8 +1053,8 @@ extern "C" size_t umb_tree_attn_workspace_bytes(int qo, int num_q_heads, int hea
 }
 
 #if UMB_ATTN_TC
-// 3-D tensor map over a K (or V) cache plane: (d, kv head, kv row) with the caller's strides, box [64 d, 1 head, 128 rows],
-// 128-byte swizzle -- one box is one 64-d atom of a tile as tcgen05.mma reads it.
+// 4-D tensor map over a K (or V) cache plane with the caller's strides, 128-byte swizzle -- one box is one whole tile (both
+// 64-d atoms) as tcgen05.mma reads it.
 typedef CUresult (*PFN_encodeTiledAttn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1039,11 +1069,13 @@ static int make_tmap_kv(CUtensorMap* map, const void* base, int D, int Hkv, int6
             return UMB_ERR_DRIVER;
         enc = reinterpret_cast<PFN_encodeTiledAttn>(sym);
     }
-    const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Hkv, (cuuint64_t)rows};
-    const cuuint64_t strides[2] = {(cuuint64_t)head_stride * sizeof(__half), (cuuint64_t)tok_stride * sizeof(__half)};
-    const cuuint32_t box[3] = {64, 1, (cuuint32_t)kTcT};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    // (d within a 64-wide atom, kv row, atom, kv head): one box = [2 atoms][kTcT rows][128 B] in shared memory
+    const cuuint64_t dims[4] = {64, (cuuint64_t)rows, (cuuint64_t)(D / 64), (cuuint64_t)Hkv};
+    const cuuint64_t strides[3] = {(cuuint64_t)tok_stride * sizeof(__half), 64 * sizeof(__half),
+                                   (cuuint64_t)head_stride * sizeof(__half)};
+    const cuuint32_t box[4] = {64, (cuuint32_t)kTcT, (cuuint32_t)(D / 64), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? UMB_OK : arg_fail(__FILE__, __LINE__, "cuTensorMapEncodeTiled(kv)");

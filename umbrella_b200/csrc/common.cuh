@@ -87,6 +87,23 @@ __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, u
         : "memory");
 }
 
+// Pure polling wait (mbarrier.test_wait never suspends the thread).  For latency-critical hand-overs in kernels with a
+// handful of warps: a try_wait that finds the phase still open parks the thread for a fixed quantum -- measured 1024 ns on
+// a B200 (profiles/r2_attn_long_context.txt: every MMA-side wait of the attention kernel took exactly 1024 ns) -- even if
+// the barrier completes a few nanoseconds later.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 // Ring-buffer cursor: stage index + phase parity.
 struct Ring {
     uint32_t stage = 0, phase = 0;
@@ -152,6 +169,14 @@ __device__ __forceinline__ void tma_tensor3d_g2s(void* smem_dst, const CUtensorM
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%2, %3, %4}], [%5], %6;"
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_tensor4d_g2s(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                                 uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
