@@ -1189,20 +1189,22 @@ extern "C" int umb_tree_attn_f16(const void* q, const void* k_cache, const void*
         }
         CUtensorMap tk, tv;
         int rc = make_tmap_kv(&tk, k_cache, head_dim, num_kv_heads, kv_bound, kv_tok_stride, kv_head_stride);
-        if (rc != UMB_OK) return rc;
-        rc = make_tmap_kv(&tv, v_cache, head_dim, num_kv_heads, kv_bound, kv_tok_stride, kv_head_stride);
-        if (rc != UMB_OK) return rc;
-        cudaStream_t st_tc = (cudaStream_t)stream;
-        UMB_CUDA(cudaFuncSetAttribute(tree_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
-        UMB_LAUNCH_PDL(tree_attn_tc_kernel, dim3(splits, num_kv_heads), dim3(kTcThreads), (size_t)kTcSmem, st_tc, tk, tv, p);
-        int launches = 1;
-        if (splits > 1) {
-            UMB_LAUNCH_PDL(tree_attn_combine_kernel<128>, dim3((unsigned)(p.Hkv * p.qo * p.G)), dim3(128), 0, st_tc, p);
-            launches = 2;
+        if (rc == UMB_OK) rc = make_tmap_kv(&tv, v_cache, head_dim, num_kv_heads, kv_bound, kv_tok_stride, kv_head_stride);
+        if (rc == UMB_OK) {
+            cudaStream_t st_tc = (cudaStream_t)stream;
+            UMB_CUDA(cudaFuncSetAttribute(tree_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+            UMB_LAUNCH_PDL(tree_attn_tc_kernel, dim3(splits, num_kv_heads), dim3(kTcThreads), (size_t)kTcSmem, st_tc, tk, tv, p);
+            int launches = 1;
+            if (splits > 1) {
+                UMB_LAUNCH_PDL(tree_attn_combine_kernel<128>, dim3((unsigned)(p.Hkv * p.qo * p.G)), dim3(128), 0, st_tc, p);
+                launches = 2;
+            }
+            count_launches(launches);
+            UMB_LAUNCH_CHECK();
+            return UMB_OK;
         }
-        count_launches(launches);
-        UMB_LAUNCH_CHECK();
-        return UMB_OK;
+        // the tensor maps could not be encoded (driver entry point missing, unusual strides): the mma.sync kernels below
+        // take the call
     }
 
 #endif
