@@ -245,3 +245,84 @@ def test_budget_tree_is_the_best_tree_of_its_size():
     assert rate > 1.08 * shipped_rate
     # a free draft model wants the deepest tree, an expensive one the shallowest
     assert max(tune_budget_tree(16, 10.0, 0.0)[0]["depth"]) > max(tune_budget_tree(16, 10.0, 20.0)[0]["depth"])
+
+
+# ---- acceptance-rate measurement (examples/construct_sequoia.py:58-90; sequoia_utils.measure_acceptance_rate) ---------
+class _TableLM:
+    """Bigram-table model with the reference's model surface: logits of a row depend on that row's token only."""
+    device = "cpu"
+
+    def __init__(self, table):
+        self.table, self.cleared = table, 0
+
+    def inference(self, input_ids, position_ids, attention_mask, storage_ids=None):
+        assert attention_mask.shape == (input_ids.shape[1], input_ids.shape[1])
+        return self.table[input_ids]
+
+    def clear(self):
+        self.cleared += 1
+
+
+def test_measure_acceptance_rate_counts_rank_matches():
+    import torch
+    from umbrella_b200 import sequoia_utils as su
+    g = torch.Generator().manual_seed(5)
+    V, width = 50, 4
+    target = torch.randn(V, V, generator=g)
+    # the draft ranks the target's arg-max at rank (token % 5): ranks 0..3 are hits of that rank, 4 is a miss
+    draft = torch.randn(V, V, generator=g) * 0.01
+    best = target.argmax(-1)
+    for t in range(V):
+        order = draft[t].argsort(descending=True)
+        r = t % 5
+        draft[t, best[t]] = (draft[t, order[r - 1]] + draft[t, order[r]]) / 2 if r > 0 else draft[t, order[0]] + 1.0
+        if r > 0 and best[t] in order[:r].tolist():
+            draft[t, best[t]] = draft[t].max() + 1.0        # already ahead: settle it at rank 0 (bookkept below)
+    data = [(torch.randint(0, V, (7,), generator=g), torch.randint(0, V, (9,), generator=g)) for _ in range(6)]
+    tm, dm = _TableLM(target), _TableLM(draft)
+    raw = su.measure_acceptance_rate(dm, tm, data, temperature=0.0, width=width, normalize=False)
+    # brute force over the rows that predict a continuation token
+    want = [0.0] * width
+    rows = 0
+    for ctx, cont in data:
+        ids = torch.cat([ctx, cont])
+        for i in range(len(ctx) - 1, len(ids) - 1):
+            tok = int(ids[i])
+            rank = draft[tok].argsort(descending=True).tolist().index(int(best[tok]))
+            if rank < width:
+                want[rank] += 1
+            rows += 1
+    assert raw == want and rows == 54
+    rate = su.measure_acceptance_rate(dm, tm, data, temperature=0.0, width=width)
+    assert rate == pytest.approx([w / rows for w in want]) and sum(rate) <= 1.0
+    assert tm.cleared == 12 and dm.cleared == 12
+    # the vector feeds the tree builder
+    gm = su.generate_sequoia_tree(3, 4, acc=[max(r, 1e-6) for r in rate])
+    assert gm["size"] == 13
+
+
+def test_measure_acceptance_rate_stochastic_rule():
+    import torch
+    from umbrella_b200 import sequoia_utils as su
+    g = torch.Generator().manual_seed(9)
+    V = 40
+    target, draft = torch.randn(V, V, generator=g) * 3, torch.randn(V, V, generator=g) * 3
+    data = [(list(range(5)), list(range(5, 17)))]
+    T, p = 0.6, 0.9
+    rate = su.measure_acceptance_rate(_TableLM(draft), _TableLM(target), data, temperature=T, topp=p,
+                                      repetition_penalty=1.0, width=V)
+    # with every rank counted the kept mass is 1 per row
+    assert sum(rate) == pytest.approx(1.0, abs=1e-5)
+    # nucleus: the kept set is the smallest prefix of the sorted distribution whose mass reaches topp
+    dist = su.target_distribution(target[:3], T, p)
+    full = torch.softmax(target[:3] / T, -1)
+    for r in range(3):
+        sp = full[r].sort(descending=True).values
+        k = int(((sp.cumsum(0) - sp) < p).sum())
+        assert int((dist[r] > 0).sum()) == k and dist[r].sum().item() == pytest.approx(1.0, abs=1e-6)
+    # the penalty moves mass away from tokens already in the prefix
+    pen = su.measure_acceptance_rate(_TableLM(draft), _TableLM(target), data, temperature=T, topp=1.0,
+                                     repetition_penalty=1.5, width=V)
+    assert sum(pen) == pytest.approx(1.0, abs=1e-5) and pen != pytest.approx(rate)
+    # greedy rule on the same tables = one-hot rows
+    assert su.target_distribution(target[:2], 0.0).sum().item() == 2.0

@@ -182,3 +182,86 @@ def expected_accept_length(gm: dict, acc: list[float] | None = None) -> float:
         for r, c in enumerate(succ[v]):
             prob[c] = prob[v] * (acc[r] if r < len(acc) else 0.0)
     return float(sum(prob))
+
+
+def target_distribution(logits: torch.Tensor, temperature: float = 0.0, topp: float = 1.0) -> torch.Tensor:
+    """What the verify step draws the committed token from, per row of ``logits`` [T, V]: one-hot arg-max for the
+    greedy engines (temperature < 0.05, static_speculation_engine.py:298-300), else softmax(logits / T) restricted to
+    the nucleus {j : mass strictly above p_j < topp} and renormalised (the set umb_sample_f32 keeps)."""
+    logits = logits.float()
+    if temperature < 0.05:
+        return torch.nn.functional.one_hot(logits.argmax(-1), logits.shape[-1]).float()
+    p = torch.softmax(logits / temperature, dim=-1)
+    if topp < 1.0:
+        sp, order = p.sort(dim=-1, descending=True)
+        keep_sorted = (sp.cumsum(-1) - sp) < topp
+        keep = torch.zeros_like(keep_sorted).scatter(-1, order, keep_sorted)
+        p = torch.where(keep, p, torch.zeros_like(p))
+        p = p / p.sum(-1, keepdim=True)
+    return p
+
+
+def rank_acceptance(draft_logits: torch.Tensor, target_logits: torch.Tensor, width: int, temperature: float = 0.0,
+                    topp: float = 1.0) -> torch.Tensor:
+    """Sum over the T rows of P(the token the target commits is the draft's rank-r candidate), r < width.  Greedy: the
+    count of rows whose target arg-max equals the draft's rank-r token -- the accumulation of
+    examples/construct_sequoia.py:79-83."""
+    cand = draft_logits.float().topk(k=width, dim=-1).indices                  # [T, width]
+    return target_distribution(target_logits, temperature, topp).gather(-1, cand).sum(dim=0)
+
+
+@torch.inference_mode()
+def measure_acceptance_rate(draft_model, target_model, dataset, temperature: float = 0.6, topp: float = 0.9,
+                            repetition_penalty: float = 1.05, width: int = 4, max_length: int | None = None,
+                            normalize: bool = True) -> list[float]:
+    """Acceptance-rate vector for ``generate_sequoia_tree(acc=...)``: acc[r] = how often the target's next token is the
+    draft's rank-r candidate, teacher-forced over ``dataset``.
+
+    The reference declares this function and leaves it empty (sequoia_utils.py:133-135); the measurement it stands for is
+    the loop of examples/construct_sequoia.py:58-90, restated here over the models' reference ``inference`` seam:
+
+    * ``dataset``: iterable of ``(context_ids, continuation_ids)`` pairs (1-D int tensors / lists).  Both models run
+      once over ``context + continuation`` with a causal mask; the rows that predict the continuation are compared.
+    * ``temperature`` / ``topp`` select the verify rule the tree is built for (``target_distribution``);
+      ``repetition_penalty`` > 1 is applied to the target's rows over the tokens that precede each row, as verify does.
+    * ``normalize=False`` returns the raw sums, which is what the reference script passes on (construct_sequoia.py:90);
+      rates (sums / rows) are the meaningful input to the tree builder: log-rates above 0 make every deeper node look
+      better than any shallower one.
+
+    Both models are ``clear()``-ed after every sample.  ``draft_model`` / ``target_model`` are model objects with the
+    reference surface (``inference``, ``clear``, ``device``); the loading of names is ``AutoModelLM``'s business.
+    """
+    from .speculation.speculation_utils import apply_repetition_penalty, make_causal_mask
+    dev = target_model.device
+    sums = torch.zeros(width, dtype=torch.float64)
+    rows_total = 0
+    for context, continuation in dataset:
+        ctx = torch.as_tensor(context, dtype=torch.long).reshape(-1)
+        cont = torch.as_tensor(continuation, dtype=torch.long).reshape(-1)
+        if cont.numel() == 0 or ctx.numel() == 0:
+            continue
+        ids = torch.cat([ctx, cont])
+        if max_length is not None and ids.numel() > max_length:
+            ids = ids[:max_length]
+        T = ids.numel()
+        n_pred = T - ctx.numel()                       # rows ctx-1 .. T-2 predict the continuation tokens
+        if n_pred <= 0:
+            continue
+        ids_dev = ids.to(dev)[None]
+        pos = torch.arange(T, device=dev)[None]
+        mask = make_causal_mask((1, T), dev)
+        store = torch.arange(T, device=dev)
+        per_model = []
+        for m in (target_model, draft_model):
+            out = m.inference(input_ids=ids_dev, position_ids=pos, attention_mask=mask, storage_ids=store)
+            per_model.append(out[0, T - n_pred - 1:T - 1].float().cpu())
+            m.clear()
+        tgt, drf = per_model
+        if repetition_penalty > 1.0 and temperature >= 0.05:
+            tgt = torch.stack([apply_repetition_penalty(ids[None, :T - n_pred + i], tgt[i:i + 1], repetition_penalty)[0]
+                               for i in range(n_pred)])
+        sums += rank_acceptance(drf, tgt, width, temperature, topp).double()
+        rows_total += n_pred
+    if normalize and rows_total:
+        sums = sums / rows_total
+    return sums.tolist()
