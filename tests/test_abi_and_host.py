@@ -326,3 +326,83 @@ def test_measure_acceptance_rate_stochastic_rule():
     assert sum(pen) == pytest.approx(1.0, abs=1e-5) and pen != pytest.approx(rate)
     # greedy rule on the same tables = one-hot rows
     assert su.target_distribution(target[:2], 0.0).sum().item() == 2.0
+
+
+# ---- streaming front-end loop (static_speculation_engine.py:470-551) ---------------------------------------------------
+class _ScriptedEngine:
+    """The members stream_generation touches, with a verify() that commits a scripted number of tokens per step."""
+    stop_distance = 4
+
+    def __init__(self, vocab, per_step, stop_after=None, room=10_000):
+        import torch
+        self.vocab, self.per_step, self.stop_after, self.room = vocab, per_step, stop_after, room
+        self.tokens = torch.zeros(1, 4096, dtype=torch.int64)
+        self.num_nodes, self.step, self.was_reset = 10, 0, False
+
+    def validate_status(self):
+        return self.num_nodes <= self.room
+
+    def build_tree(self):
+        pass
+
+    def verify(self):
+        k = self.per_step[self.step % len(self.per_step)]
+        for i in range(k):
+            self.tokens[0, self.num_nodes + i] = (self.num_nodes + i) % len(self.vocab)
+        self.num_nodes += k
+        self.step += 1
+        return self.stop_after is None or self.step < self.stop_after
+
+    def _decode(self, ids):
+        return "".join(self.vocab[i] for i in ids)
+
+    def reset(self):
+        self.was_reset = True
+
+
+def _reference_stream(engine, max_new_tokens):
+    """The reference loop, statement for statement in behaviour (static...:470-551), as the expected value."""
+    import re as _re
+    max_new_tokens = max(max_new_tokens, engine.stop_distance)
+    decode, start, ids, pos, partial, out = True, engine.num_nodes, [], 0, "", []
+    while decode and engine.validate_status():
+        begin = engine.num_nodes
+        engine.build_tree()
+        decode = engine.verify()
+        ids.extend(engine.tokens[0, begin:engine.num_nodes].tolist())
+        words = engine._decode(ids).strip().split(" ")
+        now = len(words) - 1
+        if now > pos:
+            partial += " ".join(words[pos:now]) + " "
+            out.append(partial)
+            pos = now
+        if (bool(_re.search(r'[.?!。？！]\s*$', words[-1])) and engine.num_nodes - start >= max_new_tokens - engine.stop_distance) \
+                or engine.num_nodes - start >= max_new_tokens:
+            decode = False
+    final = " ".join(words[pos:])
+    if final:
+        partial += final
+    out.append(partial)
+    return out, engine.num_nodes - start
+
+
+@pytest.mark.parametrize("per_step,max_new,stop_after,room", [
+    ([3, 1, 4, 2], 40, None, 10_000),       # runs to the token limit
+    ([2], 40, 5, 10_000),                   # the engine stops first (EOS)
+    ([5, 3], 64, None, 10_000),             # sentence end inside the stop_distance window
+    ([1], 2, None, 10_000),                 # max_new_tokens below stop_distance is raised to it
+    ([4], 200, None, 10 + 30),              # validate_status ends the loop
+])
+def test_stream_generation_follows_the_reference_protocol(per_step, max_new, stop_after, room):
+    from umbrella_b200.speculation.speculation_utils import stream_generation
+    vocab = ["ab", " cd", "e", " f", "g.", " hi", "j", " k!", " lm", "n", " o", "p?"]
+    want, want_len = _reference_stream(_ScriptedEngine(vocab, per_step, stop_after, room), max_new)
+    eng = _ScriptedEngine(vocab, per_step, stop_after, room)
+    got = list(stream_generation(eng, max_new))
+    assert [t for t, _ in got] == want
+    assert eng.num_nodes - 10 == want_len and eng.was_reset
+    assert all(p.startswith("Output Tokens ") and "| Avg Accept Tokens " in p and p.endswith(" ms ") for _, p in got)
+    # released text only ever grows, and ends as the whole decoded answer
+    texts = [t for t, _ in got]
+    assert all(b.startswith(a) for a, b in zip(texts, texts[1:]))
+    assert texts[-1] == eng._decode(eng.tokens[0, 10:eng.num_nodes].tolist()).strip()

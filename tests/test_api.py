@@ -253,10 +253,24 @@ def test_text_colors_and_logger():
 
 
 def test_reference_import_paths_resolve():
-    """the names app/api.py, app/chatbot.py and examples/*.py import."""
+    """every ``umbrella`` import statement of the reference's app/*.py and examples/*.py."""
+    statements = [
+        "from umbrella.api.client import APIClient",
+        "from umbrella.api.server import APIServer",
+        "from umbrella.logging_config import setup_logger",
+        "from umbrella.models.auto_model import AutoModelLM",
+        "from umbrella.sequoia_utils import measure_acceptance_rate, generate_sequoia_tree",
+        "from umbrella.speculation.auto_engine import AutoEngine",
+        "from umbrella.speculation.dynamic_speculation_engine import DynamicSpeculationEngine",
+        "from umbrella.speculation.speculation_utils import make_causal_mask, is_sentence_complete_regex, "
+        "find_first_element_position",
+        "from umbrella.speculation.static_speculation_engine import StaticSpeculationEngine",
+        "from umbrella.templates import Prompts, SysPrompts",
+        "from umbrella.utils import TextColors",
+    ]
+    for st in statements:
+        ns = {}
+        exec(st, ns)
     from umbrella.api.client import APIClient as C
     from umbrella.api.server import APIServer as S
-    from umbrella.logging_config import setup_logger  # noqa: F401
-    from umbrella.templates import Prompts, SysPrompts  # noqa: F401
-    from umbrella.utils import TextColors  # noqa: F401
     assert C is APIClient and S is APIServer

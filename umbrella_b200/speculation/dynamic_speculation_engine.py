@@ -24,7 +24,7 @@ import torch
 from .. import ops
 from ..models.auto_model import AutoModelLM
 from .base import BaseEngine
-from .speculation_utils import is_sentence_complete_regex, sample_topk_topp_torch
+from .speculation_utils import is_sentence_complete_regex, sample_topk_topp_torch, stream_generation
 
 
 class DynamicSpeculationEngine(BaseEngine):
@@ -330,23 +330,14 @@ class DynamicSpeculationEngine(BaseEngine):
 
     @torch.inference_mode()
     def generate_stream(self, **api_args):
-        """dynamic...:412-: yields (partial_text, perf_log) after every verify."""
+        """dynamic...:412-: yields (text released so far, perf_log) whenever a verify completed new words, and the whole
+        text at the end (``speculation_utils.stream_generation``)."""
         success = self._start(api_args)
-        if not success:
-            if success is not None:
-                self.reset()
+        if success is None:                                          # nothing to generate
             yield "", ""
             return
-        max_new_tokens = api_args.get("max_new_tokens", 128)
-        torch.cuda.synchronize()
-        t1 = time.time()
-        steps, decode, start = 0, True, self.num_nodes
-        while decode and (self.num_nodes - start) < max_new_tokens and self.validate_status():
-            self.build_tree()
-            decode = self.verify()
-            steps += 1
-            dec_len = self.num_nodes - start + 1
-            dt = time.time() - t1
-            perf = "Avg Accept Tokens {:.2f} | TPOT {:.2f} ms".format(dec_len / steps, 1000 * dt / dec_len)
-            yield self._decode(self.tokens[0, start:self.num_nodes + 1].tolist()), perf
-        self.reset()
+        if not success:
+            self.reset()
+            yield "Exceeding reserved allowed context length", "Exceeding reserved allowed context length"   # dynamic...:444
+            return
+        yield from stream_generation(self, api_args.get("max_new_tokens", 128), sync=torch.cuda.synchronize)

@@ -3,6 +3,7 @@ umbrella/speculation/speculation_utils.py the hot path and the front-ends import
 from __future__ import annotations
 
 import re
+import time
 
 import torch
 
@@ -84,3 +85,69 @@ def sample_topk_topp_torch(logits: torch.Tensor, temperature: float, topk: int, 
         q = torch.where(p > pivot, p, torch.zeros_like(p)).sum(-1, keepdim=True)
         done = done | (q[:, 0] < topp)
     return out
+
+
+class WordStream:
+    """Word-wise assembly of streamed text, as the reference's interactive front-ends do it
+    (static_speculation_engine.py:487-538, dynamic...:455-507): after every verify the whole answer so far is decoded
+    and split on spaces; every word but the last (which the next tokens may still extend) is released, and ``partial``
+    is the released text so far.  ``finish`` releases the tail."""
+
+    def __init__(self):
+        self.words = [""]
+        self.released = 0
+        self.partial = ""
+
+    def push(self, decoded_text: str) -> bool:
+        """Take the decoded answer so far; True when new complete words were released."""
+        self.words = decoded_text.strip().split(" ")
+        complete = len(self.words) - 1
+        if complete <= self.released:
+            return False
+        self.partial += " ".join(self.words[self.released:complete]) + " "
+        self.released = complete
+        return True
+
+    def finish(self) -> str:
+        tail = " ".join(self.words[self.released:])
+        self.released = len(self.words)
+        if tail:
+            self.partial += tail
+        return self.partial
+
+
+def stream_generation(engine, max_new_tokens: int, sync=None):
+    """The decode loop of ``generate_stream`` for either engine (static...:470-551): yields
+    ``(partial_text, perf_log)`` whenever a verify completed new words and once more at the end with the tail.
+
+    Stops like the reference: on the engine's own stop (EOS, ``verify() -> False``), when ``validate_status`` fails,
+    at ``max(max_new_tokens, stop_distance)`` tokens, or from ``stop_distance`` tokens before that as soon as the text
+    ends a sentence.  ``engine`` is prefilled; it is reset at the end."""
+    sync = sync or (lambda: None)
+    limit = max(max_new_tokens, engine.stop_distance)
+    sync()
+    t1 = time.time()
+    steps, decode, start = 0, True, engine.num_nodes
+    generated_ids: list[int] = []
+    stream = WordStream()
+
+    def perf_log() -> str:
+        dec_len = engine.num_nodes - start + 1
+        return "Output Tokens {} | Avg Accept Tokens {:.2f} | TPOT {:.2f} ms ".format(
+            dec_len, dec_len / max(steps, 1), 1000 * (time.time() - t1) / dec_len)
+
+    while decode and engine.validate_status():
+        begin = engine.num_nodes
+        engine.build_tree()
+        decode = engine.verify()
+        steps += 1
+        generated_ids.extend(engine.tokens[0, begin:engine.num_nodes].tolist())
+        if stream.push(engine._decode(generated_ids)):
+            yield stream.partial, perf_log()
+        done = engine.num_nodes - start
+        if done >= limit or (done >= limit - engine.stop_distance and is_sentence_complete_regex(stream.words[-1])):
+            decode = False
+    stream.finish()
+    sync()
+    yield stream.partial, perf_log()
+    engine.reset()

@@ -22,7 +22,7 @@ from .. import _lib, ops
 from ..models.auto_model import AutoModelLM
 from ..sequoia_utils import load_growmap, tree_bits_from_mask
 from .base import BaseEngine
-from .speculation_utils import is_sentence_complete_regex, sample_topk_topp_torch
+from .speculation_utils import is_sentence_complete_regex, sample_topk_topp_torch, stream_generation
 
 
 class StaticSpeculationEngine(BaseEngine):
@@ -461,7 +461,8 @@ class StaticSpeculationEngine(BaseEngine):
 
     @torch.inference_mode()
     def generate_stream(self, **api_args):
-        """static...:437-551: yields (partial_text, perf_log) after every verify."""
+        """static...:437-551: yields (text released so far, perf_log) whenever a verify completed new words, and the
+        whole text at the end (``speculation_utils.stream_generation``)."""
         self.update_generation_args(**api_args)
         input_ids = api_args.get("input_ids", None)
         max_new_tokens = api_args.get("max_new_tokens", 128)
@@ -481,15 +482,4 @@ class StaticSpeculationEngine(BaseEngine):
             self.reset()
             yield "Exceeding reserved allowed context length", "Exceeding reserved allowed context length"   # static...:469
             return
-        torch.cuda.synchronize()
-        t1 = time.time()
-        steps, decode, start = 0, True, self.num_nodes
-        while decode and (self.num_nodes - start) < max_new_tokens and self.validate_status():
-            self.build_tree()
-            decode = self.verify()
-            steps += 1
-            dec_len = self.num_nodes - start + 1
-            dt = time.time() - t1
-            perf = "Avg Accept Tokens {:.2f} | TPOT {:.2f} ms".format(dec_len / steps, 1000 * dt / dec_len)
-            yield self._decode(self.tokens[0, start:self.num_nodes + 1].tolist()), perf
-        self.reset()
+        yield from stream_generation(self, max_new_tokens, sync=torch.cuda.synchronize)
