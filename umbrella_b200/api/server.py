@@ -31,6 +31,22 @@ def _note(text: str, color: str = "cyan") -> None:
     logger.info(TextColors.colorize(text, color))
 
 
+def _brief(request) -> str:
+    """A request for the log: long token-id lists / contexts are cut (the reference prints them whole, which at a 30k-token
+    prompt is a 200 KB log line per request)."""
+    if not isinstance(request, dict):
+        return repr(request)[:200]
+    shown = {}
+    for k, v in request.items():
+        if isinstance(v, (list, tuple)) and len(v) > 16:
+            shown[k] = f"<{len(v)} items: {list(v[:8])}...>"
+        elif isinstance(v, str) and len(v) > 200:
+            shown[k] = v[:200] + f"...<{len(v)} chars>"
+        else:
+            shown[k] = v
+    return str(shown)
+
+
 def _default_engine_factory(device: str, config: dict):
     from ..speculation.auto_engine import AutoEngine
     engine = AutoEngine.from_config(device, **config)
@@ -75,7 +91,7 @@ class APIServer:
             if item is _STOP:
                 return
             addr, conn, request = item
-            _note(f"Processing message from {addr}: {request}")
+            _note(f"Processing message from {addr}: {_brief(request)}")
             try:
                 reply = {**self.engine.generate(**request), "processed": True, "response": "Processed successfully"}
             except Exception as e:  # noqa: BLE001 -- one bad request must not take the replica down
@@ -96,7 +112,7 @@ class APIServer:
             send_data(conn, dict(GREETING))
             while not self._closing.is_set():
                 request = receive_data(conn)
-                _note(f"Received dictionary from {addr}: {request}")
+                _note(f"Received dictionary from {addr}: {_brief(request)}")
                 if not isinstance(request, dict):
                     send_data(conn, {"processed": False, "response": "a request is a dict of generate() arguments"})
                     continue
