@@ -153,6 +153,8 @@ def test_pick_replica_least_loaded_then_round_robin():
     assert pick_replica([1, 0, 1, 0], 0) == 1
     assert pick_replica([2, 2, 1], 0) == 2
     assert pick_replica([3], 0) == 0
+    assert pick_replica([0, 5, 1], 0, eligible=[False, True, True]) == 2
+    assert pick_replica([0, 0], 0, eligible=[False, False]) == -1
 
 
 def test_front_spreads_requests_over_replicas():
@@ -192,20 +194,36 @@ def test_front_spreads_requests_over_replicas():
         [s.shutdown() for s in servers]
 
 
-def test_front_answers_when_a_replica_is_gone():
+def test_front_survives_a_lost_replica_and_takes_it_back():
     servers = [APIServer({}, device=f"cpu:{i}", port=0, engine_factory=make_echo_engine).start() for i in range(2)]
-    front = ReplicaFront([("127.0.0.1", s.port) for s in servers], port=0).start()
+    front = ReplicaFront([("127.0.0.1", s.port) for s in servers], port=0, retry_dead_s=0.2).start()
+    revived = None
     try:
+        lost_port = servers[1].port
         servers[1].shutdown()
         with APIClient(port=front.port, retry_seconds=0.05, max_retries=20) as c:
             outs = [c.get_output(input_ids=[i], max_new_tokens=1) for i in range(4)]
-        ok = [o for o in outs if o["processed"]]
-        lost = [o for o in outs if not o["processed"]]
-        assert ok and all(o["replica"] == 0 for o in ok)
-        assert lost and all("replica 1 unreachable" in o["response"] for o in lost)
+            # every request is answered: the one placed on the lost replica is placed again on the other
+            assert all(o["processed"] and o["replica"] == 0 for o in outs)
+            assert any(o.get("replicas_tried_before") == [1] for o in outs)
+            assert front.stats()["alive"] == [True, False] and front.stats()["in_flight"] == [0, 0]
+            # the replica comes back on its port: after retry_dead_s the front reconnects and uses it again
+            revived = APIServer({}, device="cpu:1", port=lost_port, engine_factory=make_echo_engine).start()
+            time.sleep(0.3)
+            outs = [c.get_output(input_ids=[i], max_new_tokens=1) for i in range(4)]
+            assert all(o["processed"] for o in outs) and {o["replica"] for o in outs} == {0, 1}
+            assert front.stats()["alive"] == [True, True]
+            # nobody left: the client is told, per request
+            servers[0].shutdown()
+            revived.shutdown()
+            gone = c.get_output(input_ids=[9], max_new_tokens=1)
+            assert gone["processed"] is False and "no replica reachable" in gone["response"]
+            assert gone["input_ids"] == [9]
     finally:
         front.shutdown()
-        servers[0].shutdown()
+        [s.shutdown() for s in servers]
+        if revived is not None:
+            revived.shutdown()
 
 
 @pytest.mark.timeout(120)

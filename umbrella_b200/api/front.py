@@ -36,6 +36,8 @@ class _Backend:
         self.in_flight = 0          # guarded by ReplicaFront._pick_lock
         self.served = 0
         self.sock: socket.socket | None = None
+        self.alive = False
+        self.dead_since = 0.0
 
     def connect(self, timeout_s: float) -> None:
         deadline = time.monotonic() + timeout_s
@@ -50,14 +52,30 @@ class _Backend:
                     raise
                 time.sleep(0.2)         # replicas take a while to load 37.7 GB of weights; keep knocking
         sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
-        self.sock = sock
         receive_data(sock)              # the replica's greeting
+        self.sock = sock
+        self.alive = True
 
-    def call(self, request: dict) -> dict:
+    def call(self, request: dict, reconnect_timeout_s: float) -> dict:
         with self.lock:
-            assert self.sock is not None
-            send_data(self.sock, request)
-            return receive_data(self.sock)
+            if not self.alive:
+                self.connect(reconnect_timeout_s)       # a replica that was restarted on its port comes back here
+            try:
+                send_data(self.sock, request)
+                return receive_data(self.sock)
+            except (ConnectionError, OSError, EOFError):
+                self.drop()
+                raise
+
+    def drop(self) -> None:
+        self.alive = False
+        self.dead_since = time.monotonic()
+        if self.sock is not None:
+            try:
+                self.sock.close()
+            except OSError:
+                pass
+            self.sock = None
 
     def close(self) -> None:
         if self.sock is not None:
@@ -67,28 +85,36 @@ class _Backend:
                 pass
             self.sock.close()
             self.sock = None
+        self.alive = False
 
 
-def pick_replica(in_flight: list[int], cursor: int) -> int:
-    """Least work in flight; among equals the first at or after ``cursor`` (round robin), so an idle front spreads
-    consecutive requests over all replicas instead of reusing replica 0."""
+def pick_replica(in_flight: list[int], cursor: int, eligible: list[bool] | None = None) -> int:
+    """Least work in flight among the ``eligible`` replicas (default: all); among equals the first at or after
+    ``cursor`` (round robin), so an idle front spreads consecutive requests over all replicas instead of reusing
+    replica 0.  -1 when no replica is eligible."""
     n = len(in_flight)
-    low = min(in_flight)
+    ok = [True] * n if eligible is None else eligible
+    loads = [in_flight[i] for i in range(n) if ok[i]]
+    if not loads:
+        return -1
+    low = min(loads)
     for step in range(n):
         i = (cursor + step) % n
-        if in_flight[i] == low:
+        if ok[i] and in_flight[i] == low:
             return i
     raise AssertionError("unreachable")
 
 
 class ReplicaFront:
     def __init__(self, backends: list[tuple[str, int]], port: int = 65432, host: str = "127.0.0.1", max_client: int = 64,
-                 connect_timeout_s: float = 1800.0):
+                 connect_timeout_s: float = 1800.0, retry_dead_s: float = 10.0, reconnect_timeout_s: float = 0.5):
         if not backends:
             raise ValueError("ReplicaFront needs at least one replica address")
         self.backends = [_Backend(i, h, p) for i, (h, p) in enumerate(backends)]
         self.port, self.host, self.max_client = port, host, max_client
         self.connect_timeout_s = connect_timeout_s
+        self.retry_dead_s = retry_dead_s                # a replica that dropped its connection is tried again this often
+        self.reconnect_timeout_s = reconnect_timeout_s
         self._pick_lock = threading.Lock()
         self._cursor = 0
         self._closing = threading.Event()
@@ -97,34 +123,56 @@ class ReplicaFront:
         self._accept_thread: threading.Thread | None = None
 
     # ---- placement ----------------------------------------------------------------------------------------------
-    def _acquire(self) -> _Backend:
+    def _acquire(self, exclude: set[int]) -> _Backend | None:
+        now = time.monotonic()
         with self._pick_lock:
-            i = pick_replica([b.in_flight for b in self.backends], self._cursor)
+            eligible = [b.index not in exclude and (b.alive or now - b.dead_since >= self.retry_dead_s)
+                        for b in self.backends]
+            i = pick_replica([b.in_flight for b in self.backends], self._cursor, eligible)
+            if i < 0:
+                return None
             self._cursor = (i + 1) % len(self.backends)
-            self.backends[i].in_flight += 1
-            return self.backends[i]
+            b = self.backends[i]
+            b.in_flight += 1
+            if not b.alive:
+                b.dead_since = now          # this request probes it; the others wait another retry_dead_s
+            return b
 
-    def _release(self, b: _Backend) -> None:
+    def _release(self, b: _Backend, served: bool) -> None:
         with self._pick_lock:
             b.in_flight -= 1
-            b.served += 1
+            b.served += int(served)
 
     def dispatch(self, request: dict) -> dict:
-        """Place one request, wait for its replica's answer, tag it with the replica index."""
-        b = self._acquire()
-        try:
-            reply = b.call(request)
-        except (ConnectionError, OSError, EOFError) as e:
-            reply = {**request, "processed": False, "response": f"replica {b.index} unreachable: {e}"}
-        finally:
-            self._release(b)
-        if isinstance(reply, dict):
-            reply.setdefault("replica", b.index)
-        return reply
+        """Place one request, wait for its replica's answer, tag it with the replica index.  Generation is a pure
+        function of the request (an engine is reset after every request), so a request whose replica drops the
+        connection is placed again on another one; only when no replica is left does the client get the error."""
+        failed: set[int] = set()
+        errors = []
+        while True:
+            b = self._acquire(failed)
+            if b is None:
+                return {**request, "processed": False,
+                        "response": "no replica reachable" + "".join(f"; replica {i} unreachable: {e}" for i, e in errors)}
+            try:
+                reply = b.call(request, self.reconnect_timeout_s)
+            except (ConnectionError, OSError, EOFError) as e:
+                self._release(b, served=False)
+                failed.add(b.index)
+                errors.append((b.index, e))
+                logger.error(TextColors.colorize(f"front: replica {b.index} ({b.host}:{b.port}) dropped: {e}", "red"))
+                continue
+            self._release(b, served=True)
+            if isinstance(reply, dict):
+                reply.setdefault("replica", b.index)
+                if failed:
+                    reply.setdefault("replicas_tried_before", sorted(failed))
+            return reply
 
     def stats(self) -> dict:
         with self._pick_lock:
-            return {"served": [b.served for b in self.backends], "in_flight": [b.in_flight for b in self.backends]}
+            return {"served": [b.served for b in self.backends], "in_flight": [b.in_flight for b in self.backends],
+                    "alive": [b.alive for b in self.backends]}
 
     # ---- client side: the reference protocol ---------------------------------------------------------------------
     def _handle_client(self, conn, addr) -> None:
