@@ -406,3 +406,45 @@ def test_stream_generation_follows_the_reference_protocol(per_step, max_new, sto
     texts = [t for t, _ in got]
     assert all(b.startswith(a) for a, b in zip(texts, texts[1:]))
     assert texts[-1] == eng._decode(eng.tokens[0, 10:eng.num_nodes].tolist()).strip()
+
+
+def test_dynamic_scripted_acceptance_picks_the_scripted_child_rank():
+    """DynamicScriptedAcceptance against a per-node loop: the rank-r child by draft score replaces the sampled token."""
+    import torch
+    from types import SimpleNamespace
+    from umbrella_b200.speculation.scripted import DynamicScriptedAcceptance
+    rng = np.random.default_rng(3)
+    width, depth = 4, 5
+    N, n = width * depth + 1, 17
+    acc = [0.5, 0.25, 0.15]
+    script = DynamicScriptedAcceptance(N, seed=8, max_iters=6, device="cpu", acc=acc)
+    replaced = kept = 0
+    for it in range(9):                                     # wraps around max_iters
+        parents = np.zeros(N, dtype=np.int32)
+        score = np.zeros(N, dtype=np.float32)
+        for lvl in range(depth):
+            first = 1 + lvl * width
+            prev = [0] if lvl == 0 else list(range(first - width, first))
+            for w in range(first, first + width):
+                parents[w] = rng.choice(prev)
+                score[w] = score[parents[w]] - rng.random()
+        tokens = torch.zeros(1, 64, dtype=torch.int64)
+        tokens[0, n:n + N] = torch.from_numpy(rng.integers(1000, 2000, N))
+        eng = SimpleNamespace(tree_size=N, num_nodes=n, parents=torch.from_numpy(parents),
+                              tree_score=torch.from_numpy(score), tokens=tokens)
+        sampled = torch.arange(N, dtype=torch.int64)        # stands for the target's own tokens (match no child)
+        want = script.want[it % 6].tolist()
+        got = script(eng, sampled).tolist()
+        for v in range(N):
+            kids = sorted([w for w in range(1, N) if parents[w] == v], key=lambda w: (-score[w], w))
+            if 0 <= want[v] < len(kids):
+                assert got[v] == int(tokens[0, n + kids[want[v]]]), (it, v)
+                replaced += 1
+            else:
+                assert got[v] == v
+                kept += 1
+    assert replaced > 20 and kept > 20
+    # the draws follow acc: rank r with probability acc[r], none with the rest
+    big = DynamicScriptedAcceptance(50, seed=1, max_iters=400, device="cpu", acc=acc).want.flatten()
+    freq = [float((big == r).float().mean()) for r in (0, 1, 2, -1)]
+    assert freq == pytest.approx(acc + [1 - sum(acc)], abs=0.02)

@@ -64,3 +64,45 @@ class ScriptedAcceptance:
         picked = tree_tokens.gather(0, row.clamp(min=0))
         self.last = torch.where(row >= 0, picked, sampled)      # kept for tests / cross-implementation replay
         return self.last
+
+
+class DynamicScriptedAcceptance:
+    """The same script for the dynamic engine, whose tree is regrown every iteration: per (iteration, node) a seeded
+    draw decides which child *rank* the target "chooses" (rank r with probability ``acc[r]``, none beyond); if the tree
+    holds that child its token replaces the target's sampled token at the node, else the target's own token stays (and
+    matches no child, up to chance).  A node's children are ranked by their cumulative draft score -- the tree keeps the
+    best candidates of a level, so for one parent these are its top draft tokens in order, i.e. the in-tree rank is the
+    draft rank.  Runs after the full target forward and sampling; device ops only, no host synchronisation."""
+
+    def __init__(self, tree_size: int, seed: int, max_iters: int, device, acc=None):
+        acc = DEFAULT_ACC if acc is None else acc
+        rng = np.random.default_rng(seed)
+        u = rng.random((max_iters, tree_size))
+        edges = np.cumsum(np.asarray(acc, dtype=np.float64))
+        want = np.searchsorted(edges, u, side="right")                   # rank whose interval holds u
+        want[want >= len(acc)] = -1
+        self.want = torch.from_numpy(want.astype(np.int64)).to(device)
+        self.node = torch.arange(tree_size, device=device)
+        self.it = 0
+        self.max_iters = max_iters
+
+    def reset(self):
+        self.it = 0
+
+    def child_ranks(self, parents: torch.Tensor, score: torch.Tensor) -> torch.Tensor:
+        """rank[w] = how many siblings of w (same parent, root excluded) lie ahead of it by score (ties: lower index)."""
+        node = self.node
+        same = parents[:, None] == parents[None, :]
+        ahead = (score[None, :] > score[:, None]) | ((score[None, :] == score[:, None]) & (node[None, :] < node[:, None]))
+        return (same & ahead & (node[None, :] >= 1)).sum(dim=1)
+
+    def __call__(self, engine, sampled: torch.Tensor) -> torch.Tensor:
+        N, n = engine.tree_size, engine.num_nodes
+        parents = engine.parents.to(torch.int64)
+        want = self.want[self.it % self.max_iters]
+        self.it += 1
+        match = (self.child_ranks(parents, engine.tree_score) == want[parents]) & (self.node >= 1)
+        slot = torch.where(match, parents, torch.full_like(parents, N))          # non-chosen nodes write to a spare slot
+        out = torch.cat([sampled, sampled.new_zeros(1)]).scatter(0, slot, engine.tokens[0, n:n + N])
+        self.last = out[:N]
+        return self.last
