@@ -187,7 +187,7 @@ def test_front_spreads_requests_over_replicas():
         assert sum(served) == 16 and min(served) >= 6, served          # least-in-flight keeps both replicas busy
         assert front.stats()["in_flight"] == [0, 0]
         serial = n_clients * per_client * delay                        # one engine: 1.28 s
-        assert wall < 0.75 * serial, (wall, serial)                    # two replicas: ~0.64 s + overheads
+        assert wall < 0.85 * serial, (wall, serial)                    # two replicas: ~0.64 s + overheads
         assert all(len(s.engine.threads) == 1 for s in servers)
     finally:
         front.shutdown()
