@@ -448,3 +448,34 @@ def test_dynamic_scripted_acceptance_picks_the_scripted_child_rank():
     big = DynamicScriptedAcceptance(50, seed=1, max_iters=400, device="cpu", acc=acc).want.flatten()
     freq = [float((big == r).float().mean()) for r in (0, 1, 2, -1)]
     assert freq == pytest.approx(acc + [1 - sum(acc)], abs=0.02)
+
+
+def test_graph_inference_surface():
+    """Model surface of the reference's examples (examples/bench.py:30-47): graph_inference == inference for plain models,
+    storage-id placement for cuda_graph=True models, initialize_cuda_graph clears the cache."""
+    import torch
+    from types import SimpleNamespace
+    from umbrella_b200.models.llama import Llama
+    calls = []
+
+    def fake(storage_semantics):
+        kv = SimpleNamespace(kv_offset=40, clear=lambda: calls.append("clear"))
+        m = SimpleNamespace(kv_cache=kv, storage_id_semantics=storage_semantics)
+        m.inference = lambda ids, pos, mask, store: calls.append(("inference", kv.kv_offset, ids.shape[1])) or "logits"
+        m.clear = kv.clear
+        return m
+
+    ids = torch.zeros(1, 3, dtype=torch.long)
+    plain = fake(False)
+    assert Llama.graph_inference(plain, input_ids=ids, position_ids=None, attention_mask=None,
+                                 storage_ids=torch.arange(7, 10)) == "logits"
+    assert calls[-1] == ("inference", 40, 3)                     # appended at kv_offset, storage values ignored
+    graph = fake(True)
+    Llama.graph_inference(graph, input_ids=ids, storage_ids=torch.arange(7, 10), position_ids=None, attention_mask=None)
+    assert calls[-1] == ("inference", 7, 3)                      # rows written where storage_ids says
+    with pytest.raises(ValueError):
+        Llama.graph_inference(graph, input_ids=ids, storage_ids=torch.tensor([7, 9, 10]))
+    with pytest.raises(TypeError):                               # keyword arguments only: the reference's two orders differ
+        Llama.graph_inference(graph, ids, torch.arange(7, 10))
+    Llama.initialize_cuda_graph(graph, [1, 13], n_warmups=2)
+    assert calls[-1] == "clear" and graph.graph_lengths == [1, 13]

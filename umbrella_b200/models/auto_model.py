@@ -102,6 +102,9 @@ class AutoModelLM:
             raise ValueError(f"Model type '{model_name}' is not supported. "
                              f"Supported types: {list(cls._MODEL_MAPPING.keys())}")
         # offload=True -> the paged classes of models/offload.py (LlamaOffload / LlamaAwqOffload);
-        # cuda_graph selects a graph-replay variant in the reference -- here the engines capture the
-        # whole iteration themselves over the same native forward.
-        return _make(model_name, offload=offload, **kwargs)
+        # cuda_graph selects a graph-replay variant in the reference (static KV cache written at storage_ids) -- here
+        # the engines capture the whole iteration themselves over the same native forward; the flag only selects the
+        # storage-id semantics of ``graph_inference``.
+        model = _make(model_name, offload=offload, **kwargs)
+        model.storage_id_semantics = bool(cuda_graph)      # graph_inference writes rows where storage_ids says
+        return model

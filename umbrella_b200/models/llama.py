@@ -302,6 +302,32 @@ class Llama:
             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "llama_forward_dyn")
         return logits
 
+    # ------------------------------------------------------------------ graph surface (base.py:25-31, llama.py:506-533)
+    storage_id_semantics = False        # True for a model made with ``cuda_graph=True`` (the reference's StaticKV_Cache)
+
+    def initialize_cuda_graph(self, decoding_seqlens, n_warmups: int = 12):
+        """``LlamaCudagraph.initialize_cuda_graph`` captures one torch graph per decoding length so that a forward
+        stops being ~30 eager launches per layer.  Here a forward of any length is one C call that enqueues every
+        launch, and the engines capture whole iterations, so there is nothing to capture ahead of time: the lengths
+        are recorded and, as in the reference (llama.py:519), the cache is cleared."""
+        self.graph_lengths = sorted(set(getattr(self, "graph_lengths", [])) | {int(x) for x in decoding_seqlens})
+        self.clear()
+
+    @torch.inference_mode()
+    def graph_inference(self, input_ids: torch.LongTensor, *, storage_ids: torch.LongTensor | None = None,
+                        position_ids: torch.LongTensor | None = None, attention_mask: torch.Tensor | None = None):
+        """The call the reference's examples make on every model (examples/bench.py:35-47, generate.py:55-86,
+        construct_sequoia.py:71-75), keyword arguments only (its two definitions order them differently).
+        Plain models: ``inference`` (base.py:25-31).  ``cuda_graph=True`` models: the new rows go where
+        ``storage_ids`` says (StaticKV_Cache.update_kv_cache, cache.py:150-158) -- a contiguous ascending range, which
+        becomes the append position; the attention then spans the rows up to its end, as the mask beyond is empty."""
+        if self.storage_id_semantics and storage_ids is not None and storage_ids.numel() > 0:
+            first, last = storage_ids.reshape(-1)[[0, -1]].tolist()                 # one host read
+            if last - first != storage_ids.numel() - 1:
+                raise ValueError("storage_ids must be a contiguous ascending range")
+            self.kv_cache.kv_offset = int(first)
+        return self.inference(input_ids, position_ids, attention_mask, storage_ids)
+
     # ------------------------------------------------------------------ cache ops (llama.py:136-142)
     def gather_kv_incremental(self, indices, offset: int):
         self.kv_cache.gather_kv_incremental(indices, offset)
