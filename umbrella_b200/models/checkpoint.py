@@ -62,7 +62,7 @@ def shape_from_config(path: str) -> tuple[LlamaShape, bool]:
     if rope_scaling is None and rope_params.get("rope_type", "default") != "default":
         rope_scaling = {k: v for k, v in rope_params.items() if k != "rope_theta"}
     eos = cfg.get("eos_token_id", (128001, 128008, 128009))
-    eos = tuple(eos) if isinstance(eos, (list, tuple)) else (eos,)
+    eos = list(eos) if isinstance(eos, (list, tuple)) else [eos]
     q = cfg.get("quantization_config") or {}
     awq = q.get("quant_method") == "awq"
     if awq:

@@ -42,7 +42,8 @@ class LlamaShape:
         "original_max_position_embeddings": 8192, "rope_type": "llama3"})
     tie_word_embeddings: bool = False
     group_size: int = 128
-    eos_token_id: tuple = (128001, 128008, 128009)
+    # a list, as LlamaConfig holds it (examples/generate.py:44-46 tests ``isinstance(eos_tokens, list)``)
+    eos_token_id: list = field(default_factory=lambda: [128001, 128008, 128009])
 
     @property
     def head_dim(self) -> int:
@@ -113,7 +114,8 @@ class Llama:
         self.num_key_value_heads = shape.num_key_value_heads
         self.num_key_value_groups = self.num_heads // self.num_key_value_heads
         self.num_layers = shape.num_hidden_layers if num_layers is None else num_layers
-        self.eos_tokens = list(getattr(shape, "eos_token_id", (128001, 128008, 128009)))
+        eos = getattr(shape, "eos_token_id", (128001, 128008, 128009))
+        self.eos_tokens = list(eos) if isinstance(eos, (list, tuple)) else [int(eos)]
         self.norm_variance_epsilon = shape.rms_norm_eps
         self._c_model = None
         self.layer_weights: list[dict] = []
