@@ -479,3 +479,26 @@ def test_graph_inference_surface():
         Llama.graph_inference(graph, ids, torch.arange(7, 10))
     Llama.initialize_cuda_graph(graph, [1, 13], n_warmups=2)
     assert calls[-1] == "clear" and graph.graph_lengths == [1, 13]
+
+
+def test_packaged_configs_build_engines():
+    """configs/*.json (the BASELINE workloads in the reference's config schema) go through AutoEngine.from_config; the
+    trees they name are packaged."""
+    import glob
+    import json
+    from umbrella_b200.models.llama import KNOWN_MODELS
+    from umbrella_b200.sequoia_utils import load_growmap
+    from umbrella_b200.speculation.auto_engine import AutoEngine
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "configs", "*.json")))
+    assert len(files) >= 5
+    for f in files:
+        cfg = json.load(open(f))
+        assert KNOWN_MODELS.get(cfg["model"]) and KNOWN_MODELS.get(cfg["draft_model"]), f
+        eng = AutoEngine.from_config("cuda:0", **cfg)          # construction is host-only; initialize() needs the GPU
+        assert type(eng).__name__ == {"static": "StaticSpeculationEngine", "dynamic": "DynamicSpeculationEngine"}[cfg["engine"]]
+        assert eng.max_length == cfg["max_length"] and eng.temperature == cfg["temperature"]
+        if cfg["engine"] == "static":
+            assert load_growmap(cfg["growmap_path"])["size"] >= 13
+        else:
+            assert (eng.tree_width, eng.tree_depth, eng.num_beams) == (cfg["width"], cfg["depth"], cfg["num_beams"])
