@@ -502,3 +502,24 @@ def test_packaged_configs_build_engines():
             assert load_growmap(cfg["growmap_path"])["size"] >= 13
         else:
             assert (eng.tree_width, eng.tree_depth, eng.num_beams) == (cfg["width"], cfg["depth"], cfg["num_beams"])
+
+
+def test_kv_host_layers_config_goes_to_the_paged_target_only():
+    """An engine config with "kv_host_layers" builds the target with the paged class and keeps the key away from the
+    draft (whose resident class refuses it)."""
+    import json
+    from umbrella_b200.speculation.speculation_utils import split_model_config
+    cfg = {"num_cache_layers": 0, "exit_layer": 16, "cuda_graph": True}
+    assert split_model_config(cfg, target_offload=False) == (cfg, cfg, False)
+    assert split_model_config(cfg, target_offload=True)[2] is True
+    d, t, off = split_model_config(dict(cfg, kv_host_layers=40, kv_staging_layers=3), target_offload=False)
+    assert d == cfg and t["kv_host_layers"] == 40 and t["kv_staging_layers"] == 3 and off is True
+    assert split_model_config(dict(cfg, kv_host_layers=0), target_offload=False)[2] is False
+    # the engines use it where they build their models
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("static_speculation_engine.py", "dynamic_speculation_engine.py"):
+        src = open(os.path.join(root, "umbrella_b200", "speculation", name)).read()
+        assert "split_model_config(self.config" in src and "draft_model.alloc(**draft_cfg)" in src
+    from umbrella_b200.speculation.auto_engine import AutoEngine
+    eng = AutoEngine.from_config("cuda:0", **json.load(open(os.path.join(root, "configs", "b200_stochastic_32k_host_kv.json"))))
+    assert eng.config["kv_host_layers"] == 40

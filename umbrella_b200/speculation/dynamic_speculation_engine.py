@@ -24,7 +24,8 @@ import torch
 from .. import ops
 from ..models.auto_model import AutoModelLM
 from .base import BaseEngine
-from .speculation_utils import is_sentence_complete_regex, sample_topk_topp_torch, stream_generation
+from .speculation_utils import (is_sentence_complete_regex, sample_topk_topp_torch, split_model_config,
+                                stream_generation)
 
 
 class DynamicSpeculationEngine(BaseEngine):
@@ -73,12 +74,13 @@ class DynamicSpeculationEngine(BaseEngine):
         self.tree_bits[0, 0] = 1
 
         kw = dict(batch_size=1, max_length=self.max_length, device=dev, dtype=self.dtype)
+        draft_cfg, target_cfg, target_offload = split_model_config(self.config, target_offload=True)   # dynamic...:70-80
         if draft_model is None:
             draft_model = AutoModelLM.from_pretrained(model_name=self.draft_model_name, offload=False, **kw)
-            draft_model.alloc(**self.config)
+            draft_model.alloc(**draft_cfg)
         if target_model is None:
-            target_model = AutoModelLM.from_pretrained(model_name=self.target_model_name, offload=True, **kw)
-            target_model.alloc(**self.config)
+            target_model = AutoModelLM.from_pretrained(model_name=self.target_model_name, offload=target_offload, **kw)
+            target_model.alloc(**target_cfg)
         self.draft_model, self.target_model = draft_model, target_model
         try:   # tokenizer / generation config need local HF files; token-id entry points work without
             from transformers import AutoTokenizer

@@ -151,3 +151,16 @@ def stream_generation(engine, max_new_tokens: int, sync=None):
     sync()
     yield stream.partial, perf_log()
     engine.reset()
+
+
+_TARGET_ONLY_KEYS = ("kv_host_layers", "kv_staging_layers")
+
+
+def split_model_config(config: dict, target_offload: bool) -> tuple[dict, dict, bool]:
+    """The engines hand their whole leftover config to both models' ``alloc`` (static...:92-99).  Keys that ask for
+    host-resident KV pages (north_star: 32k contexts over an offloaded KV cache; models/kv_paging.py) concern the
+    target only, and need its paged class: returns (draft alloc kwargs, target alloc kwargs, build the target with
+    ``offload=True``)."""
+    kv_host = int(config.get("kv_host_layers", 0) or 0)
+    draft_cfg = {k: v for k, v in config.items() if k not in _TARGET_ONLY_KEYS}
+    return draft_cfg, dict(config), bool(target_offload or kv_host > 0)

@@ -22,7 +22,8 @@ from .. import _lib, ops
 from ..models.auto_model import AutoModelLM
 from ..sequoia_utils import load_growmap, tree_bits_from_mask
 from .base import BaseEngine
-from .speculation_utils import is_sentence_complete_regex, sample_topk_topp_torch, stream_generation
+from .speculation_utils import (is_sentence_complete_regex, sample_topk_topp_torch, split_model_config,
+                                stream_generation)
 
 
 class StaticSpeculationEngine(BaseEngine):
@@ -88,12 +89,14 @@ class StaticSpeculationEngine(BaseEngine):
         self.branch_lists = self.growmap["branches"]
 
         kw = dict(batch_size=1, max_length=self.max_length, device=dev, dtype=self.dtype)
+        # "kv_host_layers" in the config: the target keeps that many layers' K/V pages in pinned host memory (paged class)
+        draft_cfg, target_cfg, target_offload = split_model_config(self.config, target_offload=False)
         if draft_model is None:
             draft_model = AutoModelLM.from_pretrained(model_name=self.draft_model_name, offload=False, cuda_graph=True, **kw)
-            draft_model.alloc(**self.config)
+            draft_model.alloc(**draft_cfg)
         if target_model is None:
-            target_model = AutoModelLM.from_pretrained(model_name=self.target_model_name, offload=False, **kw)
-            target_model.alloc(**self.config)
+            target_model = AutoModelLM.from_pretrained(model_name=self.target_model_name, offload=target_offload, **kw)
+            target_model.alloc(**target_cfg)
         self.draft_model, self.target_model = draft_model, target_model
 
         try:   # tokenizer / generation config need local HF files; token-id entry points work without
