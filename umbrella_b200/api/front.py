@@ -51,8 +51,12 @@ class _Backend:
                 if time.monotonic() > deadline:
                     raise
                 time.sleep(0.2)         # replicas take a while to load 37.7 GB of weights; keep knocking
-        sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
-        receive_data(sock)              # the replica's greeting
+        try:
+            sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+            receive_data(sock)          # the replica's greeting
+        except (ConnectionError, OSError, EOFError):
+            sock.close()
+            raise
         self.sock = sock
         self.alive = True
 
