@@ -292,3 +292,39 @@ def test_reference_import_paths_resolve():
     from umbrella.api.client import APIClient as C
     from umbrella.api.server import APIServer as S
     assert C is APIClient and S is APIServer
+
+
+def test_wire_golden_from_the_reference():
+    """tests/golden/wire.bin holds frames written by the reference's own send_data (oracle/make_golden_frontend.py):
+    receive_data reads them back, and send_data writes the same bytes."""
+    with open(os.path.join(HERE, "golden", "wire.json")) as f:
+        messages = json.load(f)
+    with open(os.path.join(HERE, "golden", "wire.bin"), "rb") as f:
+        raw = f.read()
+    a, b = socket.socketpair()
+    try:
+        t = threading.Thread(target=lambda: (a.sendall(raw), a.shutdown(socket.SHUT_WR)))
+        t.start()
+        got = [receive_data(b) for _ in messages]
+        t.join()
+        assert got == messages
+        with pytest.raises(ConnectionError):
+            receive_data(b)                                  # nothing after the last frame
+    finally:
+        a.close()
+        b.close()
+    a, b = socket.socketpair()
+    try:
+        for m in messages:
+            send_data(a, m)
+        a.shutdown(socket.SHUT_WR)
+        mine = b""
+        while True:
+            chunk = b.recv(1 << 16)
+            if not chunk:
+                break
+            mine += chunk
+        assert mine == raw
+    finally:
+        a.close()
+        b.close()

@@ -2,7 +2,7 @@
 (reference: umbrella/templates.py:1-47; used by app/*.py, examples/*.py and ``configs/*.json``'s "template" key).
 
 The tables are assembled from each model family's role markers instead of being written out, so the marker of a
-family is stated once; tests/golden/templates.json (made from the reference by oracle/make_golden_templates.py) pins
+family is stated once; tests/golden/templates.json (made from the reference by oracle/make_golden_frontend.py) pins
 the resulting strings byte for byte.
 """
 from __future__ import annotations
