@@ -360,52 +360,30 @@ class _ScriptedEngine:
         self.was_reset = True
 
 
-def _reference_stream(engine, max_new_tokens):
-    """The reference loop, statement for statement in behaviour (static...:470-551), as the expected value."""
-    import re as _re
-    max_new_tokens = max(max_new_tokens, engine.stop_distance)
-    decode, start, ids, pos, partial, out = True, engine.num_nodes, [], 0, "", []
-    while decode and engine.validate_status():
-        begin = engine.num_nodes
-        engine.build_tree()
-        decode = engine.verify()
-        ids.extend(engine.tokens[0, begin:engine.num_nodes].tolist())
-        words = engine._decode(ids).strip().split(" ")
-        now = len(words) - 1
-        if now > pos:
-            partial += " ".join(words[pos:now]) + " "
-            out.append(partial)
-            pos = now
-        if (bool(_re.search(r'[.?!。？！]\s*$', words[-1])) and engine.num_nodes - start >= max_new_tokens - engine.stop_distance) \
-                or engine.num_nodes - start >= max_new_tokens:
-            decode = False
-    final = " ".join(words[pos:])
-    if final:
-        partial += final
-    out.append(partial)
-    return out, engine.num_nodes - start
+def _stream_cases():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stream.json")) as f:
+        gold = json.load(f)
+    return [(gold["vocab"], gold["start"], c) for c in gold["cases"]]
 
 
-@pytest.mark.parametrize("per_step,max_new,stop_after,room", [
-    ([3, 1, 4, 2], 40, None, 10_000),       # runs to the token limit
-    ([2], 40, 5, 10_000),                   # the engine stops first (EOS)
-    ([5, 3], 64, None, 10_000),             # sentence end inside the stop_distance window
-    ([1], 2, None, 10_000),                 # max_new_tokens below stop_distance is raised to it
-    ([4], 200, None, 10 + 30),              # validate_status ends the loop
-])
-def test_stream_generation_follows_the_reference_protocol(per_step, max_new, stop_after, room):
+@pytest.mark.parametrize("vocab,start,case", _stream_cases())
+def test_stream_generation_follows_the_reference_protocol(vocab, start, case):
+    """tests/golden/stream.json: the texts the reference's own generate_stream yields (both engines, run on CPU by
+    oracle/make_golden_stream.py over the same scripted engine) -- token limit, engine stop, sentence end inside the
+    stop_distance window, max_new_tokens below stop_distance, validate_status ending the loop."""
     from umbrella_b200.speculation.speculation_utils import stream_generation
-    vocab = ["ab", " cd", "e", " f", "g.", " hi", "j", " k!", " lm", "n", " o", "p?"]
-    want, want_len = _reference_stream(_ScriptedEngine(vocab, per_step, stop_after, room), max_new)
-    eng = _ScriptedEngine(vocab, per_step, stop_after, room)
-    got = list(stream_generation(eng, max_new))
-    assert [t for t, _ in got] == want
-    assert eng.num_nodes - 10 == want_len and eng.was_reset
+    assert start == 10
+    eng = _ScriptedEngine(vocab, case["per_step"], case["stop_after"], case["room"])
+    eng.stop_distance = case["stop_distance"]
+    got = list(stream_generation(eng, case["max_new"]))
+    assert [t for t, _ in got] == case["texts"]
+    assert eng.num_nodes - start == case["committed"] and eng.was_reset
     assert all(p.startswith("Output Tokens ") and "| Avg Accept Tokens " in p and p.endswith(" ms ") for _, p in got)
-    # released text only ever grows, and ends as the whole decoded answer
     texts = [t for t, _ in got]
-    assert all(b.startswith(a) for a, b in zip(texts, texts[1:]))
-    assert texts[-1] == eng._decode(eng.tokens[0, 10:eng.num_nodes].tolist()).strip()
+    assert all(b.startswith(a) for a, b in zip(texts, texts[1:]))          # released text only ever grows
+    assert texts[-1] == eng._decode(eng.tokens[0, start:eng.num_nodes].tolist()).strip()
+
 
 
 def test_dynamic_scripted_acceptance_picks_the_scripted_child_rank():
