@@ -1,9 +1,12 @@
 """TEST INFRASTRUCTURE.  tests/golden/stream.json: what the reference's own ``generate_stream``
 (umbrella/speculation/static_speculation_engine.py:437-565, dynamic...:412-540) yields, run on CPU over an engine object
 whose model-facing methods are scripted (``verify`` commits a scripted number of tokens per step; the tokenizer maps a
-token id to a fixed word piece).  The product's ``speculation_utils.stream_generation`` must release the same texts.
+token id to a fixed word piece).  The product's ``speculation_utils.stream_generation`` must release the same texts, and its ``speculative_decoding``
+loops must print and return the same (static...:211-255).
       python oracle/make_golden_stream.py
 """
+import contextlib
+import io
 import json
 import os
 import sys
@@ -79,7 +82,18 @@ def main():
             per_engine.append(([t for t, _ in chunks], eng.final - START))
         assert per_engine[0] == per_engine[1], "the two reference engines stream differently"
         texts, committed = per_engine[0]
-        out.append(dict(case, texts=texts, committed=committed))
+        # the interactive loop (static...:211-255, dynamic...:167-213): what it prints and returns
+        printed = []
+        for cls in (sse.StaticSpeculationEngine, dse.DynamicSpeculationEngine):
+            eng = scripted(cls, case)
+            eng._prefill(None)
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                dec_len, _, steps = eng.speculative_decoding(max_new_tokens=case["max_new"])
+            printed.append((buf.getvalue(), dec_len, steps))
+        assert printed[0] == printed[1], "the two reference engines print differently"
+        out.append(dict(case, texts=texts, committed=committed, printed=printed[0][0], dec_len=printed[0][1],
+                        steps=printed[0][2]))
         print(case, "->", len(texts), "chunks,", committed, "tokens")
     with open(os.path.join(OUT, "stream.json"), "w") as f:
         json.dump({"vocab": VOCAB, "start": START, "cases": out}, f, indent=1)

@@ -501,3 +501,22 @@ def test_kv_host_layers_config_goes_to_the_paged_target_only():
     from umbrella_b200.speculation.auto_engine import AutoEngine
     eng = AutoEngine.from_config("cuda:0", **json.load(open(os.path.join(root, "configs", "b200_stochastic_32k_host_kv.json"))))
     assert eng.config["kv_host_layers"] == 40
+
+
+@pytest.mark.parametrize("engine", ["static", "dynamic"])
+def test_speculative_decoding_prints_what_the_reference_prints(engine, monkeypatch, capsys):
+    """The interactive loop of both engines (static...:211-255, dynamic...:167-213) over the scripted engine of
+    tests/golden/stream.json: same words on stdout, same (dec_len, steps) as the reference's own loops."""
+    import torch
+    if engine == "static":
+        from umbrella_b200.speculation.static_speculation_engine import StaticSpeculationEngine as cls
+    else:
+        from umbrella_b200.speculation.dynamic_speculation_engine import DynamicSpeculationEngine as cls
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    for vocab, start, case in _stream_cases():
+        eng = _ScriptedEngine(vocab, case["per_step"], case["stop_after"], case["room"])
+        eng.stop_distance = case["stop_distance"]
+        capsys.readouterr()
+        dec_len, seconds, steps = cls.speculative_decoding(eng, max_new_tokens=case["max_new"])
+        assert capsys.readouterr().out == case["printed"], case
+        assert (dec_len, steps) == (case["dec_len"], case["steps"]) and seconds >= 0
