@@ -92,8 +92,16 @@ def main():
                 dec_len, _, steps = eng.speculative_decoding(max_new_tokens=case["max_new"])
             printed.append((buf.getvalue(), dec_len, steps))
         assert printed[0] == printed[1], "the two reference engines print differently"
+        # one API request (static...:373-434, dynamic...:343-409): the result keys the server sends back
+        results = []
+        for cls in (sse.StaticSpeculationEngine, dse.DynamicSpeculationEngine):
+            eng = scripted(cls, case)
+            r = eng.generate(input_ids=[1, 2, 3], max_new_tokens=case["max_new"], temperature=0.0)
+            r.pop("time_per_output_token")
+            results.append(r)
+        assert results[0] == results[1], "the two reference engines answer differently"
         out.append(dict(case, texts=texts, committed=committed, printed=printed[0][0], dec_len=printed[0][1],
-                        steps=printed[0][2]))
+                        steps=printed[0][2], generate=results[0]))
         print(case, "->", len(texts), "chunks,", committed, "tokens")
     with open(os.path.join(OUT, "stream.json"), "w") as f:
         json.dump({"vocab": VOCAB, "start": START, "cases": out}, f, indent=1)

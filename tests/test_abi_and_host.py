@@ -520,3 +520,44 @@ def test_speculative_decoding_prints_what_the_reference_prints(engine, monkeypat
         dec_len, seconds, steps = cls.speculative_decoding(eng, max_new_tokens=case["max_new"])
         assert capsys.readouterr().out == case["printed"], case
         assert (dec_len, steps) == (case["dec_len"], case["steps"]) and seconds >= 0
+
+
+@pytest.mark.parametrize("engine", ["static", "dynamic"])
+def test_generate_answers_what_the_reference_answers(engine, monkeypatch):
+    """One API request through ``generate`` (static...:373-434, dynamic...:343-409) over the scripted engine: the same
+    generated_text / generated_tokens / avg_accept_tokens as the reference's own ``generate`` (tests/golden/stream.json);
+    ``large_model_steps`` and ``decode_seconds`` are additions."""
+    import types
+    import torch
+    if engine == "static":
+        from umbrella_b200.speculation.static_speculation_engine import StaticSpeculationEngine as cls
+    else:
+        from umbrella_b200.speculation.dynamic_speculation_engine import DynamicSpeculationEngine as cls
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    for vocab, start, case in _stream_cases():
+        eng = _ScriptedEngine(vocab, case["per_step"], case["stop_after"], case["room"])
+        eng.num_nodes, eng.device = 0, "cpu"
+        eng.update_generation_args = lambda **kw: None
+
+        def _prefill(input_ids, eng=eng):
+            assert input_ids.shape == (1, 3) and input_ids.dtype == torch.int64
+            eng.num_nodes = start
+            return True
+        eng._prefill = _prefill
+        for name in ("_empty", "_start"):
+            if hasattr(cls, name):
+                setattr(eng, name, types.MethodType(getattr(cls, name), eng))
+        got = cls.generate(eng, input_ids=[1, 2, 3], max_new_tokens=case["max_new"], temperature=0.0)
+        want = case["generate"]
+        assert {k: got[k] for k in want} == want, case
+        assert got["time_per_output_token"] >= 0 and got["large_model_steps"] >= 1 and eng.was_reset
+    # nothing to generate: the reference's empty answer (static...:381-396)
+    eng = _ScriptedEngine(["a"], [1])
+    eng.update_generation_args = lambda **kw: None
+    for name in ("_empty", "_start"):
+        if hasattr(cls, name):
+            setattr(eng, name, types.MethodType(getattr(cls, name), eng))
+    for req in (dict(input_ids=[], max_new_tokens=4), dict(context="", max_new_tokens=4), dict(input_ids=[1], max_new_tokens=0)):
+        out = cls.generate(eng, **req)
+        assert (out["generated_text"], out["generated_tokens"], out["avg_accept_tokens"], out["time_per_output_token"]) \
+            == ("", [], 0, 0)

@@ -298,7 +298,7 @@ class DynamicSpeculationEngine(BaseEngine):
             return None
         ids = torch.as_tensor(input_ids, dtype=torch.int64)
         if not ids.is_cuda:
-            ids = ids.pin_memory().to(self.device, non_blocking=True)
+            ids = ids.pin_memory().to(self.device, non_blocking=True) if torch.cuda.is_available() else ids
         return self._prefill(input_ids=ids.reshape(1, -1))
 
     @torch.inference_mode()
