@@ -4,6 +4,9 @@ One message = a 4-byte big-endian length followed by ``pickle.dumps(dict)``.  Th
 clients talk to this server and vice versa; the reading side here differs in that it insists on *exact* counts (a TCP
 ``recv`` may return fewer bytes than asked for, including for the 4-byte header) and reports a closed peer as
 ``ConnectionError`` instead of unpickling an empty buffer.
+
+The payload is a pickle because the reference's is: unpickling runs code chosen by the sender, so this protocol is for
+trusted peers only -- servers and the replica front bind to 127.0.0.1 unless told otherwise, as the reference does.
 """
 from __future__ import annotations
 
